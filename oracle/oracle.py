@@ -155,3 +155,104 @@ def run_reference(Nx, Ny, Nz, p, seed, is_oned=0, is_equalxy=0, reps=1, params=N
                     alloc=alloc, params=[int(v) for v in pv],
                     data=data.view(np.complex128).copy()))
     return boxes, tmin
+
+
+# ----------------------------------------------------------------------------
+# ctypes face of oracle/_ref/liboracle.so (offt_oracle.c)
+# ----------------------------------------------------------------------------
+MAX_GRID = 128
+_OCOMM_FIELDS = ("p1 p2 rank_x rank_y M1 M2 M3 M4 F1 F2 F3 F4 m1 m2 m3 m4 b1 b2 b3 b4").split()
+
+
+def build_oracle(force: bool = False) -> Path:
+    """compile offt_oracle.c -> _ref/liboracle.so (gcc only; runs on the GPU box too)."""
+    so = REF_DIR / "liboracle.so"
+    src = HERE / "offt_oracle.c"
+    if force or not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, (HERE / "oracle_dft.h").stat().st_mtime):
+        subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
+    return so
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = ctypes.CDLL(str(build_oracle()))
+        L = self.lib
+        L.oracle_alloc_elems.restype = ctypes.c_int64
+        L.oracle_alloc_elems.argtypes = [ctypes.c_int] * 5
+        L.oracle_comm_fill.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 8
+        L.oracle_execute.restype = ctypes.c_int
+        L.oracle_execute.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_dft_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        L.oracle_params_range.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_params_default.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p]
+        L.oracle_is_infeasible.restype = ctypes.c_int
+        L.oracle_is_infeasible.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_params_adjust.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+
+    def alloc_elems(self, Nx, Ny, Nz, p, p1) -> int:
+        return int(self.lib.oracle_alloc_elems(Nx, Ny, Nz, p, p1))
+
+    def comm(self, Nx, Ny, Nz, p, p1, rank, S=0, is_equalxy=0) -> dict:
+        buf = (ctypes.c_int * 38)()
+        self.lib.oracle_comm_fill(buf, Nx, Ny, Nz, p, p1, rank, S, is_equalxy)
+        v = list(buf)
+        d = dict(zip(_OCOMM_FIELDS, v[:20]))
+        for i, k in enumerate(("istart", "isize", "istride", "ostart", "osize", "ostride")):
+            d[k] = tuple(v[20 + 3 * i: 23 + 3 * i])
+        return d
+
+    def box(self, Nx, Ny, Nz, p, p1, rank, S=0, is_equalxy=0) -> RankBox:
+        d = self.comm(Nx, Ny, Nz, p, p1, rank, S, is_equalxy)
+        return RankBox(p=p, rank=rank, N=(Nx, Ny, Nz), p1=d["p1"], p2=d["p2"], istart=d["istart"], isize=d["isize"],
+                       istride=d["istride"], ostart=d["ostart"], osize=d["osize"], ostride=d["ostride"],
+                       alloc=self.alloc_elems(Nx, Ny, Nz, p, p1))
+
+    def params_default(self, Nx, Ny, Nz, p, is_W0=0, is_notest=0) -> list:
+        v = (ctypes.c_int * PARAM_COUNT)()
+        self.lib.oracle_params_default(Nx, Ny, Nz, p, is_W0, is_notest, v)
+        return list(v)
+
+    def params_range(self, Nx, Ny, Nz, p) -> list:
+        lists = (ctypes.c_int * (PARAM_COUNT * MAX_GRID))()
+        sizes = (ctypes.c_int * PARAM_COUNT)()
+        self.lib.oracle_params_range(Nx, Ny, Nz, p, lists, sizes)
+        return [list(lists[i * MAX_GRID: i * MAX_GRID + sizes[i]]) for i in range(PARAM_COUNT)]
+
+    def is_infeasible(self, Nx, Ny, Nz, p, v) -> tuple:
+        vv = (ctypes.c_int * PARAM_COUNT)(*v)
+        bad = ctypes.c_int(-1)
+        r = self.lib.oracle_is_infeasible(Nx, Ny, Nz, p, vv, ctypes.byref(bad))
+        return int(r), int(bad.value)
+
+    def params_adjust(self, Nx, Ny, Nz, p, is_oned, v) -> list:
+        vv = (ctypes.c_int * PARAM_COUNT)(*v)
+        self.lib.oracle_params_adjust(Nx, Ny, Nz, p, is_oned, vv)
+        return list(vv)
+
+    def resolve_params(self, Nx, Ny, Nz, p, custom=None, is_W0=0, is_notest=1) -> list:
+        """defaults, then the caller's non-negative overrides (offt-compute.c:3415-3417)."""
+        v = self.params_default(Nx, Ny, Nz, p, is_W0, is_notest)
+        for k, val in (custom or {}).items():
+            if val >= 0:
+                v[k] = val
+        return v
+
+    def execute(self, grid: np.ndarray, p: int, v: list, is_oned=0, is_equalxy=0) -> list:
+        """forward 3-D FFT of the global `grid` through the restated pipeline on p simulated
+        ranks; returns one RankBox per rank with `.data` = that rank's in-place array."""
+        Nx, Ny, Nz = grid.shape
+        boxes = [self.box(Nx, Ny, Nz, p, v[P1], r, v[S], is_equalxy) for r in range(p)]
+        arrays = [np.ascontiguousarray(scatter_input(b, grid.astype(np.complex128))) for b in boxes]
+        ptrs = (ctypes.c_void_p * p)(*[a.ctypes.data for a in arrays])
+        vv = (ctypes.c_int * PARAM_COUNT)(*v)
+        rc = self.lib.oracle_execute(Nx, Ny, Nz, p, vv, is_oned, is_equalxy, ptrs)
+        if rc != 0:
+            raise ValueError("oracle_execute rejected the arguments")
+        for b, a in zip(boxes, arrays):
+            b.data = a
+            b.params = list(v)
+        return boxes
+
+    def dft_rows(self, data: np.ndarray, n: int, stride: int, dist: int, howmany: int, sign: int = -1) -> None:
+        assert data.dtype == np.complex128 and data.flags.c_contiguous
+        self.lib.oracle_dft_rows(data.ctypes.data, n, stride, dist, howmany, sign)

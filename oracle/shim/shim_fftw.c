@@ -13,12 +13,12 @@
 #include "fftw3.h"
 #include "fftw3-mpi.h"
 
-#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
-typedef struct { double re, im; } cplx;
+#include "../oracle_dft.h"
+typedef odft_cplx cplx;
 
 enum { PLAN_C2C = 1, PLAN_R2C = 2, PLAN_COPY = 3 };
 
@@ -27,103 +27,20 @@ struct shim_fftw_plan_s {
   int n;
   int sign;
   int howmany, istride, idist, ostride, odist;
-  int nfac;
-  int fac[64];
-  cplx *tw;       /* tw[j] = exp(sign*2*pi*i*j/n), j < n */
+  odft_plan dft;
   cplx *a, *b;    /* contiguous work rows */
   fftw_iodim hd[3];
   void *plan_in, *plan_out;
 };
-
-static void factorize(struct shim_fftw_plan_s *p) {
-  int n = p->n, nf = 0;
-  while (n % 4 == 0) { p->fac[nf++] = 4; n /= 4; }
-  while (n % 2 == 0) { p->fac[nf++] = 2; n /= 2; }
-  int f;
-  for (f = 3; f * f <= n; f += 2)
-    while (n % f == 0) { p->fac[nf++] = f; n /= f; }
-  if (n > 1) p->fac[nf++] = n;
-  if (nf == 0) p->fac[nf++] = 1;
-  p->nfac = nf;
-}
-
-/* out[0..n) = DFT of in[0], in[is], ...; twiddles taken from the size-N table with step ts = N/n */
-static void dft_rec(const struct shim_fftw_plan_s *P, cplx *out, const cplx *in, int n, int is, int ts, int fi) {
-  int p = P->fac[fi];
-  int m = n / p;
-  int q, k;
-  if (m == 1) {
-    for (q = 0; q < p; q++) out[q] = in[(size_t)q * is];
-  } else {
-    for (q = 0; q < p; q++) dft_rec(P, out + (size_t)q * m, in + (size_t)q * is, m, is * p, ts * p, fi + 1);
-  }
-  const cplx *tw = P->tw;
-  if (p == 2) {
-    for (k = 0; k < m; k++) {
-      cplx w = tw[(size_t)k * ts];
-      cplx a = out[k], b = out[k + m];
-      double br = b.re * w.re - b.im * w.im, bi = b.re * w.im + b.im * w.re;
-      out[k].re = a.re + br; out[k].im = a.im + bi;
-      out[k + m].re = a.re - br; out[k + m].im = a.im - bi;
-    }
-  } else if (p == 4) {
-    /* exp(sign*i*pi/2) = sign*i */
-    double sg = (double)P->sign;
-    for (k = 0; k < m; k++) {
-      cplx w1 = tw[(size_t)k * ts], w2 = tw[(size_t)2 * k * ts], w3 = tw[(size_t)3 * k * ts];
-      cplx a = out[k], b = out[k + m], c = out[k + 2 * m], d = out[k + 3 * m];
-      double br = b.re * w1.re - b.im * w1.im, bi = b.re * w1.im + b.im * w1.re;
-      double cr = c.re * w2.re - c.im * w2.im, ci = c.re * w2.im + c.im * w2.re;
-      double dr = d.re * w3.re - d.im * w3.im, di = d.re * w3.im + d.im * w3.re;
-      double s0r = a.re + cr, s0i = a.im + ci, s1r = a.re - cr, s1i = a.im - ci;
-      double s2r = br + dr, s2i = bi + di, s3r = br - dr, s3i = bi - di;
-      /* (sign*i)*(s3) = sign*(-s3i, s3r) */
-      double jr = -sg * s3i, ji = sg * s3r;
-      out[k].re = s0r + s2r; out[k].im = s0i + s2i;
-      out[k + m].re = s1r + jr; out[k + m].im = s1i + ji;
-      out[k + 2 * m].re = s0r - s2r; out[k + 2 * m].im = s0i - s2i;
-      out[k + 3 * m].re = s1r - jr; out[k + 3 * m].im = s1i - ji;
-    }
-  } else {
-    cplx t[p];
-    int r;
-    int N = P->n;
-    for (k = 0; k < m; k++) {
-      for (q = 0; q < p; q++) {
-        cplx w = tw[((size_t)q * k * ts) % N];
-        cplx v = out[k + (size_t)q * m];
-        t[q].re = v.re * w.re - v.im * w.im;
-        t[q].im = v.re * w.im + v.im * w.re;
-      }
-      for (r = 0; r < p; r++) {
-        double sr = 0.0, si = 0.0;
-        for (q = 0; q < p; q++) {
-          /* w_p^{qr} = tw[(q*r mod p) * N/p] */
-          cplx w = tw[(size_t)((q * r) % p) * (N / p)];
-          sr += t[q].re * w.re - t[q].im * w.im;
-          si += t[q].re * w.im + t[q].im * w.re;
-        }
-        out[k + (size_t)r * m].re = sr; out[k + (size_t)r * m].im = si;
-      }
-    }
-  }
-}
 
 static struct shim_fftw_plan_s *plan_new(int kind, int n, int sign) {
   struct shim_fftw_plan_s *p = (struct shim_fftw_plan_s *)calloc(1, sizeof(*p));
   p->kind = kind; p->n = n; p->sign = sign;
   p->howmany = 1; p->istride = p->ostride = 1; p->idist = p->odist = 0;
   if (kind != PLAN_COPY) {
-    int j;
-    factorize(p);
-    p->tw = (cplx *)malloc(sizeof(cplx) * (size_t)n);
+    odft_init(&p->dft, n, sign);
     p->a = (cplx *)malloc(sizeof(cplx) * (size_t)n);
     p->b = (cplx *)malloc(sizeof(cplx) * (size_t)n);
-    for (j = 0; j < n; j++) {
-      long double ang = (long double)sign * 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
-      p->tw[j].re = (double)cosl(ang);
-      p->tw[j].im = (double)sinl(ang);
-    }
   }
   return p;
 }
@@ -171,9 +88,9 @@ static void exec_c2c(const struct shim_fftw_plan_s *p, cplx *in, cplx *out) {
     const cplx *src = in + (size_t)h * p->idist;
     cplx *dst = out + (size_t)h * p->odist;
     if (p->ostride == 1 && (const cplx *)dst != src) {
-      dft_rec(p, dst, src, n, p->istride, 1, 0);
+      odft_exec(&p->dft, dst, src, p->istride);
     } else {
-      dft_rec(p, p->b, src, n, p->istride, 1, 0);
+      odft_exec(&p->dft, p->b, src, p->istride);
       if (p->ostride == 1) memcpy(dst, p->b, sizeof(cplx) * (size_t)n);
       else for (j = 0; j < n; j++) dst[(size_t)j * p->ostride] = p->b[j];
     }
@@ -210,7 +127,7 @@ void fftw_execute_dft_r2c(const fftw_plan p, double *in, fftw_complex *out) {
   int j, n = p->n;
   cplx *o = (cplx *)out;
   for (j = 0; j < n; j++) { p->a[j].re = in[j]; p->a[j].im = 0.0; }
-  dft_rec(p, p->b, p->a, n, 1, 1, 0);
+  odft_exec(&p->dft, p->b, p->a, 1);
   for (j = 0; j <= n / 2; j++) o[j] = p->b[j];
 }
 
@@ -221,7 +138,8 @@ void fftw_execute(const fftw_plan p) {
 
 void fftw_destroy_plan(fftw_plan p) {
   if (!p) return;
-  free(p->tw); free(p->a); free(p->b); free(p);
+  if (p->kind != PLAN_COPY) odft_free(&p->dft);
+  free(p->a); free(p->b); free(p);
 }
 
 void fftw_print_plan(const fftw_plan p) {
