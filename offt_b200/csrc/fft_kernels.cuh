@@ -1,0 +1,281 @@
+// Batched 1-D Stockham-style FFT kernels for sm_100a (power-of-two lengths).
+//
+// One CTA transforms C "columns" (independent length-N transforms).  Every
+// thread keeps E complex points in registers; a transform of length
+// N = R0*R1*R2*R3 runs as up to four register-butterfly stages (radix 2..32)
+// with a shared-memory exchange between consecutive stages.  The first stage
+// loads straight from HBM into registers and the last stage stores straight
+// from registers, so each point crosses HBM exactly once in each direction.
+//
+// Index algebra (decimation in frequency, digits k_s of the output index):
+//   stage s works on N/R_s butterflies beta = n' + M_s*K, n' < M_s = N/(R_0..R_s),
+//   K = k_0 + R_0*k_1 + ... (digits produced so far); it reads the R_s points
+//   n' + M_s*i of sub-problem K, multiplies output k_s by w_N^(P_s*n'*k_s),
+//   P_s = R_0..R_{s-1}, and files it for butterfly beta' = n'' + M_{s+1}*(K + P_s*k_s)
+//   of the next stage as its input i = n' / M_{s+1} (n'' = n' % M_{s+1}).
+//   The shared layout is [i][beta'] with row pitch N/R_{s+1} + PAD_s, so the
+//   reading side is always unit-stride in beta'.  After the last stage the
+//   output index is k = beta + (N/R_last)*k_last: unit-stride in beta again.
+//
+// Addressing is a two-level affine map on both sides (see FftMap), which is what
+// fuses the reference's pack / unpack loops (offt-compute.c:1015-1032, 1100-1116,
+// 1307-1311, 1382-1385, 1773-1776, 2055-2058, 2447-2450, 2686-2689) into the
+// transform's own loads and stores.  Lanes run either along the transform index
+// ("n-fast", contiguous rows) or along the column index ("c-fast", strided
+// axis); when the two sides differ the result is turned through shared memory.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <utility>
+
+#include "roots32.h"
+
+namespace offtb {
+
+template <typename T> struct cx;
+template <> struct __align__(16) cx<double> { double x, y; };
+template <> struct __align__(8) cx<float> { float x, y; };
+
+// element (n, b) of a batch lives at
+//   off + (n >> n_lg)*n_hi + (n & ((1<<n_lg)-1))*n_lo + b0*s0 + b1*s1 + b2*s2,
+//   b = b0 + B0*(b1 + B1*b2),  all in complex elements.  B0, B1 need not be powers of two
+//   (ragged tiles), the split of n is (blocks of an even division always are).
+struct FftMap {
+  long long off;
+  long long n_hi, n_lo;
+  long long s0, s1, s2;
+  int n_lg;
+  unsigned B0, B1;
+};
+
+struct FftArgs {
+  const void *in;
+  void *out;
+  const void *tw;  // cx<T>[N]: exp(-2*pi*i*j/N)
+  FftMap im, om;
+  int c_log;       // log2(columns per CTA)
+  int load_cfast, store_cfast;
+  int conj;        // 1: backward transform via conj(FFT(conj(x)))
+  // Ry rule of the reference (offt-compute.c:1484, 1708): transform a column only if
+  // lo <= (x % 10) < hi, x = ry_x0 + batch digit `ry_level`; ry_level < 0: always
+  int ry_level, ry_x0, ry_lo, ry_hi;
+};
+
+constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+constexpr int brev(int v, int radix) {
+  int r = 0;
+  for (int m = radix >> 1; m > 0; m >>= 1) { r = (r << 1) | (v & 1); v >>= 1; }
+  return r;
+}
+
+template <int N_, int E_, int R0_, int R1_, int R2_, int R3_, int PAD0_, int PAD1_, int PAD2_, int MAXT_, int MINB_>
+struct FftCfg {
+  static constexpr int N = N_, E = E_, T = N_ / E_, MAXT = MAXT_, MINB = MINB_;
+  static constexpr int NS = R1_ == 1 ? 1 : (R2_ == 1 ? 2 : (R3_ == 1 ? 3 : 4));
+  static constexpr int radix(int s) { return s == 0 ? R0_ : s == 1 ? R1_ : s == 2 ? R2_ : R3_; }
+  static constexpr int pad(int s) { return s == 0 ? PAD0_ : s == 1 ? PAD1_ : PAD2_; }
+  static constexpr int P(int s) { return s == 0 ? 1 : P(s - 1) * radix(s - 1); }   // digits already produced
+  static constexpr int M(int s) { return N_ / (P(s) * radix(s)); }                 // sub-problem length left
+  static constexpr int pitch(int s) { return N_ / radix(s + 1) + pad(s); }         // exchange s -> s+1
+  static constexpr int xsize(int s) { return radix(s + 1) * pitch(s); }
+  static constexpr int colsize() {
+    int m = N_ + 1;  // the turn buffer of transposing launches
+    for (int s = 0; s + 1 < NS; ++s) m = xsize(s) > m ? xsize(s) : m;
+    return m;
+  }
+  static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+  static_assert(E_ % R0_ == 0 && E_ % R1_ == 0 && E_ % R2_ == 0 && E_ % R3_ == 0, "E must be a multiple of every radix");
+};
+
+__device__ __forceinline__ cx<double> ldg_cx(const cx<double> *p) {
+  double2 d = __ldg(reinterpret_cast<const double2 *>(p));
+  return {d.x, d.y};
+}
+__device__ __forceinline__ cx<float> ldg_cx(const cx<float> *p) {
+  float2 d = __ldg(reinterpret_cast<const float2 *>(p));
+  return {d.x, d.y};
+}
+template <typename T> __device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> csub(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> w) {
+  return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x};
+}
+
+// a * exp(-2*pi*i*K32/32), K32 known at compile time
+template <typename T, int K32> __device__ __forceinline__ cx<T> mul_root(cx<T> a) {
+  if constexpr (K32 == 0) return a;
+  else if constexpr (K32 == 8) return {a.y, -a.x};
+  else if constexpr (K32 == 4) {
+    constexpr T h = (T)Root32<4>::re;
+    return {(a.x + a.y) * h, (a.y - a.x) * h};
+  } else if constexpr (K32 == 12) {
+    constexpr T h = (T)Root32<4>::re;
+    return {(a.y - a.x) * h, -(a.x + a.y) * h};
+  } else {
+    constexpr T c = (T)Root32<K32>::re, s = (T)Root32<K32>::im;
+    return {a.x * c - a.y * s, a.x * s + a.y * c};
+  }
+}
+
+// in-place radix-R DFT of v[OFF..OFF+R) by radix-2 DIF splitting; result k ends at OFF + brev(k, R)
+template <typename T, int R, int OFF, int J> __device__ __forceinline__ void bfly_pair(cx<T> *v) {
+  cx<T> a = v[OFF + J], b = v[OFF + J + R / 2];
+  v[OFF + J] = cadd(a, b);
+  v[OFF + J + R / 2] = mul_root<T, J * (32 / R)>(csub(a, b));
+}
+template <typename T, int R, int OFF, int... J> __device__ __forceinline__ void bfly_level(cx<T> *v, std::integer_sequence<int, J...>) {
+  (bfly_pair<T, R, OFF, J>(v), ...);
+}
+template <typename T, int R, int OFF> __device__ __forceinline__ void bfly(cx<T> *v) {
+  if constexpr (R > 1) {
+    bfly_level<T, R, OFF>(v, std::make_integer_sequence<int, R / 2>{});
+    bfly<T, R / 2, OFF>(v);
+    bfly<T, R / 2, OFF + R / 2>(v);
+  }
+}
+template <typename T, int R, int... U> __device__ __forceinline__ void bfly_all(cx<T> *v, std::integer_sequence<int, U...>) {
+  (bfly<T, R, U * R>(v), ...);
+}
+
+__device__ __forceinline__ long long map_n(const FftMap &m, int n) {
+  return (long long)(n >> m.n_lg) * m.n_hi + (long long)(n & ((1 << m.n_lg) - 1)) * m.n_lo;
+}
+__device__ __forceinline__ long long map_b(const FftMap &m, unsigned b) {
+  const unsigned b0 = b % m.B0, r = b / m.B0;
+  const unsigned b1 = r % m.B1, b2 = r / m.B1;
+  return m.off + (long long)b0 * m.s0 + (long long)b1 * m.s1 + (long long)b2 * m.s2;
+}
+__device__ __forceinline__ unsigned digit_b(const FftMap &m, unsigned b, int level) {
+  if (level == 0) return b % m.B0;
+  const unsigned r = b / m.B0;
+  return level == 1 ? r % m.B1 : r / m.B1;
+}
+
+template <typename T, class CFG, int S>
+__device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, cx<T> *sm, const cx<T> *__restrict__ gin,
+                                          cx<T> *__restrict__ gout, int t, int s_mul, int s_base, T cj) {
+  constexpr int N = CFG::N, E = CFG::E, TT = CFG::T, NS = CFG::NS;
+  constexpr int R = CFG::radix(S), NU = E / R, P = CFG::P(S), M = CFG::M(S);
+  const cx<T> *__restrict__ tw = (const cx<T> *)a.tw;
+
+  // ---- inputs
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int beta = t + TT * u;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if constexpr (S == 0) {
+        cx<T> e = gin[map_n(a.im, beta + (N / R) * i)];
+        e.y *= cj;
+        v[u * R + i] = e;
+      } else {
+        v[u * R + i] = sm[(i * CFG::pitch(S - 1) + beta) * s_mul + s_base];
+      }
+    }
+  }
+  // ---- butterflies
+  bfly_all<T, R>(v, std::make_integer_sequence<int, NU>{});
+
+  if constexpr (S < NS - 1) {
+    constexpr int Rn = CFG::radix(S + 1), Mn = M / Rn;
+    if constexpr (S > 0) __syncthreads();  // everyone has read this stage's inputs
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int beta = t + TT * u;
+      const int np = beta & (M - 1), K = beta / M;
+      const int npp = np & (Mn - 1), inext = np / Mn;
+      const int abase = inext * CFG::pitch(S) + npp + Mn * K;
+#pragma unroll
+      for (int pos = 0; pos < R; ++pos) {
+        const int k = brev(pos, R);
+        cx<T> e = v[u * R + pos];
+        if (k != 0) e = cmul(e, ldg_cx(&tw[P * np * k]));
+        sm[(abase + Mn * P * k) * s_mul + s_base] = e;
+      }
+    }
+    __syncthreads();
+    fft_stage<T, CFG, S + 1>(v, a, sm, gin, gout, t, s_mul, s_base, cj);
+  } else {
+    // ---- last stage: output index beta + (N/R)*k
+    if (a.load_cfast == a.store_cfast) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int beta = t + TT * u;
+#pragma unroll
+        for (int pos = 0; pos < R; ++pos) {
+          cx<T> e = v[u * R + pos];
+          e.y *= cj;
+          gout[map_n(a.om, beta + (N / R) * brev(pos, R))] = e;
+        }
+      }
+    } else {
+      // turn through shared memory: [column][k] with odd pitch N+1
+      if constexpr (NS > 1) __syncthreads();
+      const int C = 1 << a.c_log;
+      const int c = a.load_cfast ? (int)(threadIdx.x & (C - 1)) : (int)(threadIdx.x / TT);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int beta = t + TT * u;
+#pragma unroll
+        for (int pos = 0; pos < R; ++pos) sm[c * (N + 1) + beta + (N / R) * brev(pos, R)] = v[u * R + pos];
+      }
+      __syncthreads();
+      const unsigned bblock = blockIdx.x << a.c_log;
+      const int nthreads = TT << a.c_log;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int flat = threadIdx.x + e * nthreads;
+        int cc, k;
+        if (a.store_cfast) { cc = flat & (C - 1); k = flat >> a.c_log; }
+        else { k = flat & (N - 1); cc = flat / N; }
+        cx<T> val = sm[cc * (N + 1) + k];
+        val.y *= cj;
+        ((cx<T> *)a.out)[map_b(a.om, bblock + cc) + map_n(a.om, k)] = val;
+      }
+    }
+  }
+}
+
+template <typename T, class CFG>
+__global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_constant__ FftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
+  constexpr int E = CFG::E, TT = CFG::T, N = CFG::N;
+  const int C = 1 << a.c_log;
+  const int tid = threadIdx.x;
+  int t, c;
+  if (a.load_cfast) { c = tid & (C - 1); t = tid >> a.c_log; }
+  else { t = tid & (TT - 1); c = tid / TT; }
+  const unsigned bblock = blockIdx.x << a.c_log;
+
+  // Ry rule: a CTA-uniform choice between transforming and merely moving its columns
+  if (a.ry_level >= 0) {
+    const int x = a.ry_x0 + (int)digit_b(a.im, bblock, a.ry_level);
+    const int r = x % 10;
+    if (!(a.ry_lo <= r && r < a.ry_hi)) {
+      const int nthreads = TT << a.c_log;
+#pragma unroll 4
+      for (int e = 0; e < E; ++e) {
+        const int flat = tid + e * nthreads;
+        int cc, n;
+        if (a.load_cfast) { cc = flat & (C - 1); n = flat >> a.c_log; }
+        else { n = flat & (N - 1); cc = flat / N; }
+        ((cx<T> *)a.out)[map_b(a.om, bblock + cc) + map_n(a.om, n)] =
+            ((const cx<T> *)a.in)[map_b(a.im, bblock + cc) + map_n(a.im, n)];
+      }
+      return;
+    }
+  }
+
+  const cx<T> *gin = (const cx<T> *)a.in + map_b(a.im, bblock + c);
+  cx<T> *gout = (cx<T> *)a.out + map_b(a.om, bblock + c);
+  const int s_mul = a.load_cfast ? C : 1;
+  const int s_base = a.load_cfast ? c : c * CFG::colsize();
+  const T cj = a.conj ? (T)-1 : (T)1;
+  cx<T> v[E];
+  fft_stage<T, CFG, 0>(v, a, sm, gin, gout, t, s_mul, s_base, cj);
+}
+
+}  // namespace offtb

@@ -1,0 +1,217 @@
+"""-m gpu: the CUDA path through the C-ABI library against the oracle.
+
+Tolerances are BASELINE.json's: relative L2 error <= 1e-12 in double, <= 1e-5 in single
+(single is compared with the double oracle).  Layouts are compared through
+ostart/osize/ostride, exactly where the reference driver reads its output (run-fft.c:477-478).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from gpu_helpers import gather_input, gpu_forward, local_world
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = {64: 1e-12, 32: 1e-5}
+P = O  # parameter indices
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; the library has no CPU path")
+    return torch
+
+
+# ---------------------------------------------------------------- the 1-D kernels alone
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_rows_contiguous_and_strided(oracle, n, bits):
+    torch = _torch()
+    import offt_b200 as ob
+    rng = np.random.default_rng(n)
+    rows = 16
+    a = (rng.uniform(-1, 1, (rows, n)) + 1j * rng.uniform(-1, 1, (rows, n)))
+    want = a.copy()
+    oracle.dft_rows(want, n, 1, n, rows, -1)
+    cdt = torch.complex128 if bits == 64 else torch.complex64
+    with local_world(1):
+        d = torch.from_numpy(a).to("cuda").to(cdt).contiguous()
+        ob.fft_rows(d, n, 1, n, rows, sign=-1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy(), want) < TOL[bits]
+        # same rows laid out along the slow axis: element j of row h at h + j*rows
+        d = torch.from_numpy(np.ascontiguousarray(a.T)).to("cuda").to(cdt).contiguous()
+        ob.fft_rows(d, n, rows, 1, rows, sign=-1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy().T, want) < TOL[bits]
+        # backward transform of the result returns n * input
+        ob.fft_rows(d, n, rows, 1, rows, sign=+1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy().T / n, a) < TOL[bits]
+
+
+@pytest.mark.parametrize("n", [16, 64, 512, 1024])
+def test_raw_maps_split_transpose_ry(oracle, n):
+    """the address maps that fuse pack/unpack: split transform index, batch digits (also
+    non power-of-two), transposing store, the Ry rule's copy path."""
+    torch = _torch()
+    import offt_b200 as ob
+    rng = np.random.default_rng(7 * n)
+    B0, B1, B2 = 8, 3, 2            # batch digits; B1 = 3 is a ragged tile
+    nb = B0 * B1 * B2
+    src = rng.uniform(-1, 1, (B2, B1, n, B0)) + 1j * rng.uniform(-1, 1, (B2, B1, n, B0))   # column index fastest
+    want = np.fft.fft(src, axis=2)
+    with local_world(1):
+        d_in = torch.from_numpy(src).to("cuda").contiguous()
+        # (1) strided in place
+        im = [0, 0, 0, B0, B0, 1, B1, n * B0, B1 * n * B0]
+        d = d_in.clone()
+        ob.fft_launch_raw(d, d, n, nb, im, im, load_cfast=1, store_cfast=1)
+        assert O.rel_l2(d.cpu().numpy(), want) < 1e-12
+        # (2) transposing store: out[b2][b1][b0][n] (transform index contiguous)
+        om = [0, 0, 0, 1, B0, n, B1, n * B0, B1 * n * B0]
+        out = torch.zeros_like(d_in)
+        ob.fft_launch_raw(d_in, out, n, nb, im, om, load_cfast=1, store_cfast=0)
+        got = out.cpu().numpy().reshape(B2, B1, B0, n).transpose(0, 1, 3, 2)
+        assert O.rel_l2(got, want) < 1e-12
+        # (3) and back: load contiguous rows, store strided
+        back = torch.zeros_like(d_in)
+        ob.fft_launch_raw(out, back, n, nb, om, im, sign=+1, load_cfast=0, store_cfast=1)
+        assert O.rel_l2(back.cpu().numpy() / n, src) < 1e-12
+        # (4) split transform index on the store side: n -> (n // q, n % q) with block stride
+        q = n // 4
+        om = [0, q, B2 * B1 * q * B0, B0, B0, 1, B1, q * B0, B1 * q * B0]
+        out = torch.zeros_like(d_in)
+        ob.fft_launch_raw(d_in, out, n, nb, im, om, load_cfast=1, store_cfast=1)
+        got = out.cpu().numpy().reshape(4, B2, B1, q, B0).transpose(1, 2, 0, 3, 4).reshape(B2, B1, n, B0)
+        assert O.rel_l2(got, want) < 1e-12
+        # (5) Ry rule on digit 2 (x): x = 7 + b2, transform only if x % 10 < 8 -> b2 = 0 only
+        d = d_in.clone()
+        ob.fft_launch_raw(d, d, n, nb, im, im, load_cfast=1, store_cfast=1, ry=(2, 7, 0, 8))
+        got = d.cpu().numpy()
+        assert O.rel_l2(got[0], want[0]) < 1e-12
+        assert np.array_equal(got[1], src[1])
+
+
+# ---------------------------------------------------------------- whole plans vs the oracle
+CASES = [
+    # N, p, is_oned, is_equalxy, custom
+    ((16, 8, 32), 1, 0, 0, {P.P1: 1}),
+    ((16, 8, 32), 1, 1, 0, {P.P1: 1, P.S: 1}),
+    ((16, 16, 8), 1, 0, 1, {P.P1: 1}),
+    ((16, 8, 32), 4, 1, 0, {P.P1: 4}),
+    ((16, 8, 32), 4, 1, 0, {P.P1: 4, P.S: 1}),
+    ((16, 8, 32), 4, 1, 0, {P.P1: 1}),
+    ((16, 8, 32), 4, 1, 0, {P.P1: 1, P.S: 1}),
+    ((16, 16, 8), 4, 1, 1, {P.P1: 1}),
+    ((16, 16, 8), 4, 1, 1, {P.P1: 4}),
+    ((16, 16, 16), 4, 0, 0, {P.P1: 2}),
+    ((16, 16, 16), 4, 0, 0, {P.P1: 2, P.S: 1}),
+    ((16, 16, 16), 4, 0, 1, {P.P1: 2}),
+    ((16, 16, 16), 4, 0, 0, {P.P1: 4}),
+    ((16, 16, 16), 4, 0, 0, {P.P1: 1, P.S: 1}),
+    ((32, 64, 16), 8, 0, 0, {P.P1: 2, P.T1: 4, P.T2: 2}),
+    ((32, 64, 16), 8, 0, 0, {P.P1: 4, P.S: 1, P.RY: 3}),
+    ((32, 32, 32), 4, 0, 0, {P.P1: 2, P.T1: 3, P.T2: 5, P.W1: 1, P.W2: 3}),     # ragged last tiles
+    ((32, 32, 32), 4, 0, 0, {P.P1: 2, P.T1: 16, P.T2: 16, P.W1: 0, P.W2: 0, P.RY: 0}),
+    ((32, 32, 32), 4, 0, 0, {P.P1: 2, P.T1: 1, P.T2: 1, P.W1: 10, P.W2: 10, P.RY: 10, P.S: 1}),
+    ((64, 128, 256), 8, 0, 0, {P.P1: 2}),
+    ((256, 64, 128), 8, 1, 0, {P.P1: 8}),
+    ((128, 128, 128), 2, 1, 0, {P.P1: 2, P.S: 1}),
+]
+
+
+@pytest.mark.parametrize("N,p,oned,eq,custom", CASES)
+def test_plan_matches_oracle(oracle, N, p, oned, eq, custom):
+    _torch()
+    grid = O.grid_values(5, *N)
+    v = oracle.resolve_params(*N, p, custom)
+    want = oracle.execute(grid, p, v, oned, eq)
+    got, launches, back = gpu_forward(grid, p, custom, oned, eq, inverse_too=True)
+    assert launches > 0
+    for a, b in zip(got, want):
+        assert a.params == b.params
+        assert (a.istart, a.isize, a.istride, a.ostart, a.osize, a.ostride, a.alloc) == \
+               (b.istart, b.isize, b.istride, b.ostart, b.osize, b.ostride, b.alloc)
+    A, B = O.gather_output(got), O.gather_output(want)
+    assert not np.isnan(A).any()
+    assert O.rel_l2(A, B) < 1e-12
+    # forward -> backward returns N * input in the input layout
+    rt = gather_input(got, back) / np.prod(N)
+    assert O.rel_l2(rt, grid) < 1e-12
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("uneven")])
+def test_plan_matches_reference_fixture(name):
+    """fixtures = outputs of the unmodified reference (tests/golden/make_golden.py)"""
+    _torch()
+    g = load_golden(name)
+    grid = O.grid_values(g["seed"], *g["N"])
+    got, _, _ = gpu_forward(grid, g["p"], g["custom"], g["is_oned"], g["is_equalxy"])
+    assert got[0].params == g["params"]
+    assert O.rel_l2(O.gather_output(got), O.gather_output(g["boxes"])) < 1e-12
+
+
+@pytest.mark.parametrize("N,p,oned,custom", [((64, 32, 128), 1, 0, {P.P1: 1}), ((32, 64, 64), 4, 0, {P.P1: 2}),
+                                             ((64, 64, 64), 4, 1, {P.P1: 4, P.S: 1})])
+def test_single_precision(oracle, N, p, oned, custom):
+    _torch()
+    grid = O.grid_values(9, *N)
+    want = O.gather_output(oracle.execute(grid, p, oracle.resolve_params(*N, p, custom), oned, 0))
+    got, _, back = gpu_forward(grid, p, custom, oned, 0, bits=32, inverse_too=True)
+    assert O.rel_l2(O.gather_output(got, np.complex64), want) < 1e-5
+    assert O.rel_l2(gather_input(got, back, np.complex64) / np.prod(N), grid) < 1e-5
+
+
+def test_host_arrays_and_ramp_known_answer():
+    """the reference driver's own usage: calloc'd host array, ramp input, read (0,0,z<4) through
+    ostride (run-fft.c:46-61, 452-503)"""
+    _torch()
+    N = (64, 64, 64)
+    got, _, _ = gpu_forward(O.ramp_values(*N), 1, {P.P1: 1}, host_arrays=True)
+    b = got[0]
+    vals = [b.data[z * b.ostride[2]] for z in range(4)]
+    n = 64
+    want = [n ** 3 * (n - 1) / 2 * 111 + 0j] + [n ** 3 / (np.exp(-2j * np.pi * k / n) - 1) for k in (1, 2, 3)]
+    np.testing.assert_allclose(vals, want, rtol=1e-12)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (512^3 complex128, one GPU): size-independent checks -
+    a plane wave gives one spike, Parseval, and forward->backward returns N*x."""
+    torch = _torch()
+    import offt_b200 as ob
+    n = 512
+    with local_world(1):
+        plan = ob.Plan(n, n, n, is_notest=1, custom={P.P1: 1, P.S: 1})
+        x = torch.arange(n, device="cuda", dtype=torch.float64)
+        ph = 2 * np.pi * (3 * x[:, None, None] + 5 * x[None, :, None] + 7 * x[None, None, :]) / n
+        a = torch.polar(torch.ones_like(ph), ph).contiguous()
+        del ph
+        plan.execute(a)
+        assert abs(a[3, 5, 7].item() - n ** 3) < 1e-3
+        a[3, 5, 7] = 0
+        assert a.abs().max().item() < 1e-4
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        a = torch.view_as_complex(torch.rand((n, n, n, 2), device="cuda", dtype=torch.float64, generator=g) * 2 - 1).contiguous()
+        ref = a.clone()
+        e_in = (ref.abs() ** 2).sum().item()
+        plan.execute(a)
+        e_out = (a.abs() ** 2).sum().item()
+        assert abs(e_out / (n ** 3) - e_in) / e_in < 1e-12
+        plan.execute_inverse(a)
+        a /= n ** 3
+        err = (torch.linalg.vector_norm(a - ref) / torch.linalg.vector_norm(ref)).item()
+        assert err < 1e-12
+        plan.fin()
+
+
+def test_unsupported_inputs_fail_loudly():
+    _torch()
+    import offt_b200 as ob
+    with local_world(1):
+        with pytest.raises(ob.OfftError):
+            ob.Plan(12, 10, 9, custom={P.P1: 1})            # not powers of two
+        with pytest.raises(ob.OfftError):
+            ob.Plan(16, 16, 16, is_r2c=1, custom={P.P1: 1})  # r2c not implemented
+    with local_world(3):
+        with pytest.raises(ob.OfftError):
+            ob.Plan(16, 16, 16, custom={P.P1: 3}, rank=0)   # uneven split
