@@ -37,6 +37,7 @@ const char *offtb_last_error(void);
 /* 1 (default): fatal conditions print and exit(-1) like the reference (offt-compute.c:3440-3443);
  * 0: the void entry points return after recording the error (bindings poll offtb_last_error) */
 int offtb_set_exit_on_error(int on);
+void offtb_clear_error(void);
 
 /* ---- plan options (set between offt_3d_init and the first execute) -------- */
 /* precision for plans created afterwards: 64 (default, the reference's only mode) or 32 */

@@ -55,6 +55,7 @@ def _load():
     L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
     ll, i, vp, d = C.c_longlong, C.c_int, C.c_void_p, C.c_double
     L.offtb_last_error.restype = C.c_char_p
+    L.offtb_clear_error.restype = None
     L.offt_3d_init.restype = C.POINTER(OfftPlan)
     L.offt_3d_init.argtypes = [i, i, i, vp, vp] + [i] * 11 + [C.POINTER(OfftParams)]
     L.offt_3d_execute.restype = None
@@ -214,8 +215,9 @@ class Plan:
 
     def execute(self, array):
         ptr = _ptr(array)
-        lib.offt_3d_execute(self.po, ptr, ptr, 0)
-        if _err_pending():
+        lib.offtb_clear_error()
+        lib.offt_3d_execute(self.po, ptr, ptr, 0)   # void, like the reference: a failure leaves a message
+        if _err():
             raise OfftError(f"offt_3d_execute: {_err()}")
 
     def execute_inverse(self, array):
@@ -255,17 +257,6 @@ class Plan:
             self.fin()
         except Exception:
             pass
-
-
-_last_seen_error = [b""]
-
-
-def _err_pending() -> bool:
-    """the reference's execute is void; a failure shows as a new error string"""
-    e = lib.offtb_last_error() or b""
-    new = e != _last_seen_error[0] and e != b""
-    _last_seen_error[0] = e
-    return new
 
 
 def execute_group(plans, arrays, inverse=False):

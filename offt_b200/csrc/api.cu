@@ -220,16 +220,14 @@ double offtb_fft_launch_raw(const void *in, void *out, int n, int bits, int sign
   while ((1 << slot) < n) ++slot;
   void *&tw = tw_cache[slot][bits == 64 ? 0 : 1];
   if (!tw) {
-    std::vector<double> hd(2 * (size_t)n);
-    std::vector<float> hf(2 * (size_t)n);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int j = 0; j < n; ++j) {
-      const long double ang = two_pi * (long double)j / (long double)n;
-      hd[2 * j] = (double)cosl(ang); hd[2 * j + 1] = (double)(-sinl(ang));
-      hf[2 * j] = (float)cosl(ang); hf[2 * j + 1] = (float)(-sinl(ang));
-    }
-    if (cudaMalloc(&tw, (size_t)n * esz) != cudaSuccess) { set_error("cudaMalloc twiddles"); return -1.0; }
-    cudaMemcpy(tw, bits == 64 ? (void *)hd.data() : (void *)hf.data(), (size_t)n * esz, cudaMemcpyHostToDevice);
+    std::vector<long double> tab(2 * (size_t)n + 2);
+    const int count = fft_twiddle_table(n, bits, tab.data());
+    const size_t cnt = (size_t)std::max(count, 1);
+    std::vector<double> hd(2 * cnt);
+    std::vector<float> hf(2 * cnt);
+    for (size_t j = 0; j < 2 * (size_t)count; ++j) { hd[j] = (double)tab[j]; hf[j] = (float)tab[j]; }
+    if (cudaMalloc(&tw, cnt * esz) != cudaSuccess) { set_error("cudaMalloc twiddles"); return -1.0; }
+    cudaMemcpy(tw, bits == 64 ? (void *)hd.data() : (void *)hf.data(), cnt * esz, cudaMemcpyHostToDevice);
   }
   FftArgs a;
   memset(&a, 0, sizeof(a));

@@ -17,6 +17,12 @@ static cudaError_t launch_one(const FftArgs &args, long long nbatch, cudaStream_
   const int C = 1 << args.c_log;
   const size_t smem = (size_t)C * CFG::colsize() * sizeof(cx<T>);
   static size_t configured = 0;   // per instantiation
+  static bool carved = false;
+  if (!carved) {
+    // these kernels live on shared memory, not on L1: take the largest shared carve-out
+    cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carved = true;
+  }
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -101,6 +107,8 @@ cudaError_t OFFTB_CAT(fft_launch_, OFFTB_INST_N)(int prec, const FftArgs &args, 
 void OFFTB_CAT(fft_info_, OFFTB_INST_N)(int prec, FftKernelInfo *info) {
   info->N = CfgD::N; info->E = CfgD::E; info->T = CfgD::T; info->maxt = CfgD::MAXT;
   info->colsize = prec == PREC_F64 ? CfgD::colsize() : CfgF::colsize();
+  info->ns = CfgD::NS;
+  for (int s = 0; s < 4; ++s) info->radix[s] = CfgD::radix(s);
 }
 
 }  // namespace offtb

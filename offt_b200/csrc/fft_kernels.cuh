@@ -53,7 +53,7 @@ struct FftMap {
 struct FftArgs {
   const void *in;
   void *out;
-  const void *tw;  // cx<T>[N]: exp(-2*pi*i*j/N)
+  const void *tw;  // cx<T>[<N]: the per-stage tables of FftCfg::twoff, see fft_twiddle_table()
   FftMap im, om;
   int c_log;       // log2(columns per CTA)
   int load_cfast, store_cfast;
@@ -80,6 +80,8 @@ struct FftCfg {
   static constexpr int M(int s) { return N_ / (P(s) * radix(s)); }                 // sub-problem length left
   static constexpr int pitch(int s) { return N_ / radix(s + 1) + pad(s); }         // exchange s -> s+1
   static constexpr int xsize(int s) { return radix(s + 1) * pitch(s); }
+  // compact per-stage twiddle tables: stage s holds exp(-2*pi*i*n'/(R_s*M_s)), n' < M_s, at twoff(s)
+  static constexpr int twoff(int s) { return s == 0 ? 0 : twoff(s - 1) + M(s - 1); }
   static constexpr int colsize() {
     int m = N_ + 1;  // the turn buffer of transposing launches
     for (int s = 0; s + 1 < NS; ++s) m = xsize(s) > m ? xsize(s) : m;
@@ -187,11 +189,14 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, 
       const int np = beta & (M - 1), K = beta / M;
       const int npp = np & (Mn - 1), inext = np / Mn;
       const int abase = inext * CFG::pitch(S) + npp + Mn * K;
+      // w^k for k = 1..R-1 by repeated multiplication from one coalesced table load
+      const cx<T> w1 = ldg_cx(&tw[CFG::twoff(S) + np]);
+      cx<T> w = w1;
+      sm[abase * s_mul + s_base] = v[u * R];
 #pragma unroll
-      for (int pos = 0; pos < R; ++pos) {
-        const int k = brev(pos, R);
-        cx<T> e = v[u * R + pos];
-        if (k != 0) e = cmul(e, ldg_cx(&tw[P * np * k]));
+      for (int k = 1; k < R; ++k) {
+        const cx<T> e = cmul(v[u * R + brev(k, R)], w);
+        if (k + 1 < R) w = cmul(w, w1);
         sm[(abase + Mn * P * k) * s_mul + s_base] = e;
       }
     }

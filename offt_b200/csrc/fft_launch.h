@@ -9,7 +9,13 @@ enum Precision { PREC_F64 = 64, PREC_F32 = 32 };
 
 struct FftKernelInfo {
   int N, E, T, colsize, maxt;   // colsize: shared-memory elements per column
+  int ns, radix[4];             // stage count and radices
 };
+
+// Host copy of the kernel's twiddle tables for length N (interleaved re, im in long double):
+// for every stage s but the last, M_s entries exp(-2*pi*i*n'/(R_s*M_s)), concatenated.
+// Returns the number of complex entries written (< N); out must hold 2*N long doubles.
+int fft_twiddle_table(int N, int prec, long double *out);
 
 // Fills `info` for length N; returns false if N is not a supported length.
 bool fft_kernel_info(int N, int prec, FftKernelInfo *info);

@@ -97,18 +97,14 @@ int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
 namespace {
 
 int make_twiddles(int N, int prec, void **dev) {
-  std::vector<double> hd;
-  std::vector<float> hf;
-  const long double two_pi = 6.283185307179586476925286766559005768L;
-  if (prec == PREC_F64) hd.resize(2 * (size_t)N); else hf.resize(2 * (size_t)N);
-  for (int j = 0; j < N; ++j) {
-    // reduce the angle to the first octant so that every entry is accurate to the last bit
-    const long double ang = two_pi * (long double)j / (long double)N;
-    const long double c = cosl(ang), s = -sinl(ang);
-    if (prec == PREC_F64) { hd[2 * j] = (double)c; hd[2 * j + 1] = (double)s; }
-    else { hf[2 * j] = (float)c; hf[2 * j + 1] = (float)s; }
-  }
-  const size_t bytes = (size_t)N * (prec == PREC_F64 ? 16 : 8);
+  std::vector<long double> tab(2 * (size_t)N + 2);
+  const int count = fft_twiddle_table(N, prec, tab.data());
+  if (count < 0) { set_error("no kernel for length %d", N); return -1; }
+  const size_t n = (size_t)std::max(count, 1);
+  std::vector<double> hd(2 * n);
+  std::vector<float> hf(2 * n);
+  for (size_t j = 0; j < 2 * (size_t)count; ++j) { hd[j] = (double)tab[j]; hf[j] = (float)tab[j]; }
+  const size_t bytes = n * (prec == PREC_F64 ? 16 : 8);
   OFFTB_CUDA(cudaMalloc(dev, bytes));
   OFFTB_CUDA(cudaMemcpy(*dev, prec == PREC_F64 ? (void *)hd.data() : (void *)hf.data(), bytes, cudaMemcpyHostToDevice));
   return 0;

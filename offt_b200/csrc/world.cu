@@ -43,6 +43,8 @@ const char *offtb_last_error(void) { return last_error(); }
 
 int offtb_set_exit_on_error(int on) { g_exit_on_error = on; return 0; }
 
+void offtb_clear_error(void) { g_error[0] = 0; }
+
 int offtb_get_unique_id(void *id128) {
   static_assert(sizeof(ncclUniqueId) <= OFFTB_UNIQUE_ID_BYTES, "unique id does not fit");
   ncclUniqueId id;

@@ -73,6 +73,7 @@ int main(int argc, char **argv) {
     MPI_Barrier(MPI_COMM_WORLD);
     t += MPI_Wtime();
     if (t < tmin) tmin = t;
+    if (!rank) { printf("ref_dump t_rep %d %.6f\n", r, t); fflush(stdout); }
   }
   if (!rank) printf("ref_dump t_min %.6f\n", tmin);
   if (strcmp(prefix, "-") != 0) {
