@@ -7,7 +7,8 @@ import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "lib" / "libofft_b200.so"
+# OFFTB_LIB selects a variant build of the same library (tools/variants.sh); the default is the product
+LIB_PATH = Path(os.environ.get("OFFTB_LIB") or HERE / "lib" / "libofft_b200.so")
 PARAM_COUNT = 24
 GES = 16
 PARAM_NAMES = ("P1 T1 W1 Px1 Py1 Fz FP1 Ux1 Uz1 FU1 Fy1 Ry T2 W2 Pz2 Px2 Fy2 FP2 Uz2 Uy2 FU2 Fx V S").split()
@@ -52,7 +53,7 @@ def _load():
     if not LIB_PATH.exists():
         raise OfftError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")
-    L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(str(LIB_PATH))
     ll, i, vp, d = C.c_longlong, C.c_int, C.c_void_p, C.c_double
     L.offtb_last_error.restype = C.c_char_p
     L.offtb_clear_error.restype = None

@@ -4,7 +4,7 @@
 #define OFFT_NO_MINMAX
 #endif
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include "nccl_dyn.h"
 
 #include <string>
 #include <vector>
@@ -35,7 +35,7 @@ void fatal_or_return(const char *where);
   do {                                                                                     \
     ncclResult_t r__ = (call);                                                             \
     if (r__ != ncclSuccess) {                                                              \
-      offtb::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+      offtb::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, offtb::nccl_api()->GetErrorString(r__)); \
       return -1;                                                                           \
     }                                                                                      \
   } while (0)

@@ -3,6 +3,9 @@
 #include "fft_configs.h"
 #include "fft_launch.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 #ifndef OFFTB_INST_N
 #error "compile with -DOFFTB_INST_N=<length>"
 #endif
@@ -12,26 +15,55 @@ namespace offtb {
 #define OFFTB_CAT2(a, b) a##b
 #define OFFTB_CAT(a, b) OFFTB_CAT2(a, b)
 
+// Ring depth and grid of one launch.  The ring wants two tiles in flight behind the one being
+// transformed (depth 3) when shared memory allows; the grid is one wave of resident CTAs, each
+// walking its share of the tiles.  OFFTB_DEPTH / OFFTB_CTAS_PER_SM override both for experiments.
 template <typename T, class CFG>
-static cudaError_t launch_one(const FftArgs &args, long long nbatch, cudaStream_t stream) {
+static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStream_t stream) {
+  FftArgs args = args_in;
   const int C = 1 << args.c_log;
-  const size_t smem = (size_t)C * CFG::colsize() * sizeof(cx<T>);
-  static size_t configured = 0;   // per instantiation
-  static bool carved = false;
-  if (!carved) {
+  const int threads = CFG::T * C;
+  const size_t slot = (size_t)C * CFG::colsize() * sizeof(cx<T>);
+  static int sm_count = 0, smem_optin = 0, env_depth = -1, env_ctas = -1;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const char *e = getenv("OFFTB_DEPTH");
+    env_depth = e ? atoi(e) : 0;
+    e = getenv("OFFTB_CTAS_PER_SM");
+    env_ctas = e ? atoi(e) : 0;
     // these kernels live on shared memory, not on L1: take the largest shared carve-out
     cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carved = true;
+    cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
   }
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long ntiles = nbatch >> args.c_log;
+  if (ntiles <= 0) return cudaSuccess;
+  if (ntiles > 2147483647LL) return cudaErrorInvalidConfiguration;
+  if (slot > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
+  // deepest ring that still leaves 16 warps resident per SM (the butterflies need them); else no ring
+  const long long per_cta = (ntiles + sm_count - 1) / sm_count;   // tiles a CTA will see at least
+  int depth = args.depth > 0 ? args.depth : env_depth, occ = 0;
+  if (depth > 0) {
+    depth = std::min<int>(depth, std::min<int>(4, (int)(smem_optin / slot)));
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
     if (e != cudaSuccess) return e;
-    configured = smem;
+  } else {
+    for (depth = 3; depth >= 1; --depth) {
+      if (slot * depth > (size_t)smem_optin || (depth > 1 && per_cta < depth)) continue;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
+      if (e != cudaSuccess) return e;
+      if (occ * threads >= 512 || depth == 1) break;
+    }
   }
-  const long long grid = nbatch >> args.c_log;
-  if (grid <= 0) return cudaSuccess;
-  if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-  fft_kernel<T, CFG><<<(unsigned)grid, CFG::T * C, smem, stream>>>(args);
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  args.depth = depth;
+  args.ntiles = (unsigned)ntiles;
+  const size_t smem = slot * depth;
+  if (env_ctas > 0) occ = std::min(occ, env_ctas);
+  const long long grid = std::min<long long>(ntiles, (long long)occ * sm_count);
+  fft_kernel<T, CFG><<<(unsigned)grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,14 @@
 // loads straight from HBM into registers and the last stage stores straight
 // from registers, so each point crosses HBM exactly once in each direction.
 //
+// The kernel is persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps
+// the inputs of the next `depth - 1` tiles in flight with cp.async (LDGSTS) into a ring of
+// shared-memory slots while it transforms the current one.  Every thread copies exactly the points
+// it will consume into private slots ([point][thread], conflict-free), so landing needs only
+// cp.async.wait_group, no barrier; once the points are in registers the slot becomes the tile's
+// exchange buffer.  HBM reads therefore overlap the butterflies, the exchanges and the stores
+// of the previous tiles without costing registers.
+//
 // Index algebra (decimation in frequency, digits k_s of the output index):
 //   stage s works on N/R_s butterflies beta = n' + M_s*K, n' < M_s = N/(R_0..R_s),
 //   K = k_0 + R_0*k_1 + ... (digits produced so far); it reads the R_s points
@@ -56,6 +64,8 @@ struct FftArgs {
   const void *tw;  // cx<T>[<N]: the per-stage tables of FftCfg::twoff, see fft_twiddle_table()
   FftMap im, om;
   int c_log;       // log2(columns per CTA)
+  int depth;       // shared-memory ring slots (1: no prefetch)
+  unsigned ntiles; // batch / columns per CTA
   int load_cfast, store_cfast;
   int conj;        // 1: backward transform via conj(FFT(conj(x)))
   // Ry rule of the reference (offt-compute.c:1484, 1708): transform a column only if
@@ -82,6 +92,8 @@ struct FftCfg {
   static constexpr int xsize(int s) { return radix(s + 1) * pitch(s); }
   // compact per-stage twiddle tables: stage s holds exp(-2*pi*i*n'/(R_s*M_s)), n' < M_s, at twoff(s)
   static constexpr int twoff(int s) { return s == 0 ? 0 : twoff(s - 1) + M(s - 1); }
+  // twiddles a thread keeps in registers: one per butterfly of every stage but the last
+  static constexpr int twregs(int s) { return s <= 0 ? 0 : twregs(s - 1) + E_ / radix(s - 1); }
   static constexpr int colsize() {
     int m = N_ + 1;  // the turn buffer of transposing launches
     for (int s = 0; s + 1 < NS; ++s) m = xsize(s) > m ? xsize(s) : m;
@@ -98,6 +110,22 @@ __device__ __forceinline__ cx<double> ldg_cx(const cx<double> *p) {
 __device__ __forceinline__ cx<float> ldg_cx(const cx<float> *p) {
   float2 d = __ldg(reinterpret_cast<const float2 *>(p));
   return {d.x, d.y};
+}
+__device__ __forceinline__ void cp_async_cx(cx<double> *smem_dst, const cx<double> *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_cx(cx<float> *smem_dst, const cx<float> *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's groups are still in flight (pending < 4)
+__device__ __forceinline__ void cp_async_wait(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
 }
 template <typename T> __device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ cx<T> csub(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
@@ -156,25 +184,18 @@ __device__ __forceinline__ unsigned digit_b(const FftMap &m, unsigned b, int lev
 }
 
 template <typename T, class CFG, int S>
-__device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, cx<T> *sm, const cx<T> *__restrict__ gin,
-                                          cx<T> *__restrict__ gout, int t, int s_mul, int s_base, T cj) {
+__device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg, const FftArgs &a, cx<T> *sm,
+                                          cx<T> *__restrict__ gout, unsigned bblock, int t, int s_mul, int s_base, T cj) {
   constexpr int N = CFG::N, E = CFG::E, TT = CFG::T, NS = CFG::NS;
   constexpr int R = CFG::radix(S), NU = E / R, P = CFG::P(S), M = CFG::M(S);
-  const cx<T> *__restrict__ tw = (const cx<T> *)a.tw;
 
-  // ---- inputs
+  // ---- inputs (stage 0 arrives in registers)
+  if constexpr (S > 0) {
 #pragma unroll
-  for (int u = 0; u < NU; ++u) {
-    const int beta = t + TT * u;
+    for (int u = 0; u < NU; ++u) {
+      const int beta = t + TT * u;
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      if constexpr (S == 0) {
-        cx<T> e = gin[map_n(a.im, beta + (N / R) * i)];
-        e.y *= cj;
-        v[u * R + i] = e;
-      } else {
-        v[u * R + i] = sm[(i * CFG::pitch(S - 1) + beta) * s_mul + s_base];
-      }
+      for (int i = 0; i < R; ++i) v[u * R + i] = sm[(i * CFG::pitch(S - 1) + beta) * s_mul + s_base];
     }
   }
   // ---- butterflies
@@ -189,8 +210,8 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, 
       const int np = beta & (M - 1), K = beta / M;
       const int npp = np & (Mn - 1), inext = np / Mn;
       const int abase = inext * CFG::pitch(S) + npp + Mn * K;
-      // w^k for k = 1..R-1 by repeated multiplication from one coalesced table load
-      const cx<T> w1 = ldg_cx(&tw[CFG::twoff(S) + np]);
+      // w^k for k = 1..R-1 by repeated multiplication from the thread's resident twiddle
+      const cx<T> w1 = wreg[CFG::twregs(S) + u];
       cx<T> w = w1;
       sm[abase * s_mul + s_base] = v[u * R];
 #pragma unroll
@@ -201,7 +222,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, 
       }
     }
     __syncthreads();
-    fft_stage<T, CFG, S + 1>(v, a, sm, gin, gout, t, s_mul, s_base, cj);
+    fft_stage<T, CFG, S + 1>(v, wreg, a, sm, gout, bblock, t, s_mul, s_base, cj);
   } else {
     // ---- last stage: output index beta + (N/R)*k
     if (a.load_cfast == a.store_cfast) {
@@ -227,7 +248,6 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, 
         for (int pos = 0; pos < R; ++pos) sm[c * (N + 1) + beta + (N / R) * brev(pos, R)] = v[u * R + pos];
       }
       __syncthreads();
-      const unsigned bblock = blockIdx.x << a.c_log;
       const int nthreads = TT << a.c_log;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -243,44 +263,100 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const FftArgs &a, 
   }
 }
 
+// the thread's resident twiddles: entry twregs(s) + u is exp(-2*pi*i*n'/(R_s*M_s)) for its butterfly u of stage s
+template <typename T, class CFG, int S>
+__device__ __forceinline__ void load_twiddles(cx<T> *wreg, const cx<T> *__restrict__ tw, int t) {
+  if constexpr (S < CFG::NS - 1) {
+    constexpr int NU = CFG::E / CFG::radix(S), M = CFG::M(S);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) wreg[CFG::twregs(S) + u] = ldg_cx(&tw[CFG::twoff(S) + ((t + CFG::T * u) & (M - 1))]);
+    load_twiddles<T, CFG, S + 1>(wreg, tw, t);
+  }
+}
+
 template <typename T, class CFG>
 __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_constant__ FftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
-  constexpr int E = CFG::E, TT = CFG::T, N = CFG::N;
+  cx<T> *sm_all = reinterpret_cast<cx<T> *>(smem_raw);
+  constexpr int E = CFG::E, TT = CFG::T, N = CFG::N, R0 = CFG::radix(0), NU0 = E / R0;
   const int C = 1 << a.c_log;
   const int tid = threadIdx.x;
+  const int nthreads = TT << a.c_log;
   int t, c;
   if (a.load_cfast) { c = tid & (C - 1); t = tid >> a.c_log; }
   else { t = tid & (TT - 1); c = tid / TT; }
-  const unsigned bblock = blockIdx.x << a.c_log;
-
-  // Ry rule: a CTA-uniform choice between transforming and merely moving its columns
-  if (a.ry_level >= 0) {
-    const int x = a.ry_x0 + (int)digit_b(a.im, bblock, a.ry_level);
-    const int r = x % 10;
-    if (!(a.ry_lo <= r && r < a.ry_hi)) {
-      const int nthreads = TT << a.c_log;
-#pragma unroll 4
-      for (int e = 0; e < E; ++e) {
-        const int flat = tid + e * nthreads;
-        int cc, n;
-        if (a.load_cfast) { cc = flat & (C - 1); n = flat >> a.c_log; }
-        else { n = flat & (N - 1); cc = flat / N; }
-        ((cx<T> *)a.out)[map_b(a.om, bblock + cc) + map_n(a.om, n)] =
-            ((const cx<T> *)a.in)[map_b(a.im, bblock + cc) + map_n(a.im, n)];
-      }
-      return;
-    }
-  }
-
-  const cx<T> *gin = (const cx<T> *)a.in + map_b(a.im, bblock + c);
-  cx<T> *gout = (cx<T> *)a.out + map_b(a.om, bblock + c);
+  const int slot_elems = C * CFG::colsize();
   const int s_mul = a.load_cfast ? C : 1;
   const int s_base = a.load_cfast ? c : c * CFG::colsize();
   const T cj = a.conj ? (T)-1 : (T)1;
-  cx<T> v[E];
-  fft_stage<T, CFG, 0>(v, a, sm, gin, gout, t, s_mul, s_base, cj);
+  const int depth = a.depth;
+
+  constexpr int NW = CFG::twregs(CFG::NS - 1) > 0 ? CFG::twregs(CFG::NS - 1) : 1;
+  cx<T> wreg[NW];
+  load_twiddles<T, CFG, 0>(wreg, (const cx<T> *)a.tw, t);
+
+  // this thread's E points of `tile` -> its private places in ring slot `slot`
+  auto prefetch = [&](unsigned tile, int slot) {
+    if (tile < a.ntiles) {
+      const cx<T> *gin = (const cx<T> *)a.in + map_b(a.im, (tile << a.c_log) + c);
+      cx<T> *dst = sm_all + slot * slot_elems + tid;
+#pragma unroll
+      for (int u = 0; u < NU0; ++u)
+#pragma unroll
+        for (int i = 0; i < R0; ++i)
+          cp_async_cx(dst + (u * R0 + i) * nthreads, gin + map_n(a.im, t + TT * u + (N / R0) * i));
+    }
+    cp_async_commit();
+  };
+
+  unsigned tile = blockIdx.x;
+  for (int d = 0; d + 1 < depth; ++d) prefetch(tile + d * gridDim.x, d);
+  int slot = 0;
+  for (; tile < a.ntiles; tile += gridDim.x) {
+    cx<T> *sm = sm_all + slot * slot_elems;
+    if (depth == 1) {
+      __syncthreads();           // the previous tile's exchange data has been consumed
+      prefetch(tile, 0);
+      cp_async_wait(0);
+    } else {
+      cp_async_wait(depth - 2);  // this tile has landed (the younger groups may still fly)
+    }
+    cx<T> v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      cx<T> x = sm[e * nthreads + tid];
+      x.y *= cj;
+      v[e] = x;
+    }
+    if (depth > 1 || CFG::NS > 1 || a.load_cfast != a.store_cfast) __syncthreads();   // the slot now serves as exchange buffer
+    if (depth > 1) {
+      const int ahead = slot == 0 ? depth - 1 : slot - 1;   // the slot the previous tile has just released
+      prefetch(tile + (unsigned)(depth - 1) * gridDim.x, ahead);
+    }
+    const unsigned bblock = tile << a.c_log;
+    cx<T> *gout = (cx<T> *)a.out + map_b(a.om, bblock + c);
+
+    // Ry rule: a tile-uniform choice between transforming and merely moving its columns
+    bool transform = true;
+    if (a.ry_level >= 0) {
+      const int r = (a.ry_x0 + (int)digit_b(a.im, bblock, a.ry_level)) % 10;
+      transform = a.ry_lo <= r && r < a.ry_hi;
+    }
+    if (transform) {
+      fft_stage<T, CFG, 0>(v, wreg, a, sm, gout, bblock, t, s_mul, s_base, cj);
+    } else {
+#pragma unroll
+      for (int u = 0; u < NU0; ++u)
+#pragma unroll
+        for (int i = 0; i < R0; ++i) {
+          cx<T> e = v[u * R0 + i];
+          e.y *= cj;   // undo the conjugation of the load
+          gout[map_n(a.om, t + TT * u + (N / R0) * i)] = e;
+        }
+    }
+    slot = slot + 1 == depth ? 0 : slot + 1;
+  }
+  cp_async_wait(0);
 }
 
 }  // namespace offtb

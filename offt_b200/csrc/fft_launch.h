@@ -20,6 +20,9 @@ int fft_twiddle_table(int N, int prec, long double *out);
 // Fills `info` for length N; returns false if N is not a supported length.
 bool fft_kernel_info(int N, int prec, FftKernelInfo *info);
 
+// log2 of the columns one CTA transforms (see fft_launch.cu)
+int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long n_stride_elems);
+
 // Launches ceil(nbatch / 2^c_log) CTAs.  nbatch must be a multiple of 2^c_log.
 // Returns cudaSuccess or the launch error.
 cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream);

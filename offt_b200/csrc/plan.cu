@@ -142,19 +142,7 @@ cudaEvent_t pool_event(Engine &E) {
 }
 
 int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
-  const long long smem_cap = 160 * 1024;
-  long long cmax = std::max(1, info.maxt / info.T);
-  cmax = std::min<long long>(cmax, std::max<long long>(1, smem_cap / ((long long)info.colsize * (long long)E.esz)));
-  long long c = 1;
-  if (L.load_cfast || L.store_cfast) {
-    // columns must stay inside one contiguous run of the lowest batch digit
-    const long long want = E.prec == PREC_F64 ? 8 : 16;
-    while (c * 2 <= want && c * 2 <= cmax && L.im.B0 % (unsigned)(c * 2) == 0) c *= 2;
-  } else {
-    const long long want = std::max(1, 256 / info.T);
-    while (c * 2 <= want && c * 2 <= cmax && L.nbatch % (c * 2) == 0) c *= 2;
-  }
-  return lg2(c);
+  return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, std::max(L.im.n_lo, L.om.n_lo));
 }
 
 int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
@@ -324,13 +312,15 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bo
       OFFTB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
     } else {
       const ncclDataType_t ty = E.prec == PREC_F64 ? ncclDouble : ncclFloat;
-      OFFTB_NCCL(ncclGroupStart());
+      const NcclApi *nc = nccl_api();
+      if (!nc) return -1;
+      OFFTB_NCCL(nc->GroupStart());
       for (size_t j = 0; j < members.size(); ++j) {
         if ((int)j == me) continue;
-        OFFTB_NCCL(ncclSend(src + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
-        OFFTB_NCCL(ncclRecv(dst + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
+        OFFTB_NCCL(nc->Send(src + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
+        OFFTB_NCCL(nc->Recv(dst + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
       }
-      OFFTB_NCCL(ncclGroupEnd());
+      OFFTB_NCCL(nc->GroupEnd());
       OFFTB_CUDA(cudaMemcpyAsync(dst + (size_t)me * bytes, src + (size_t)me * bytes, bytes, cudaMemcpyDeviceToDevice, st));
     }
     if (E.stage_timing) { cudaEventRecord(e1, st); E.timed.push_back({phase == 1 ? ST_X1 : ST_X2, {e0, e1}}); }

@@ -26,7 +26,7 @@ double agree_max(double x) {
   static double *d = nullptr;
   if (!d) cudaMalloc(&d, sizeof(double));
   cudaMemcpy(d, &x, sizeof(double), cudaMemcpyHostToDevice);
-  ncclAllReduce(d, d, 1, ncclDouble, ncclMax, w.nccl, 0);
+  nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclMax, w.nccl, 0);
   cudaMemcpy(&x, d, sizeof(double), cudaMemcpyDeviceToHost);
   return x;
 }

@@ -48,7 +48,9 @@ void offtb_clear_error(void) { g_error[0] = 0; }
 int offtb_get_unique_id(void *id128) {
   static_assert(sizeof(ncclUniqueId) <= OFFTB_UNIQUE_ID_BYTES, "unique id does not fit");
   ncclUniqueId id;
-  OFFTB_NCCL(ncclGetUniqueId(&id));
+  const NcclApi *nc = nccl_api();
+  if (!nc) return -1;
+  OFFTB_NCCL(nc->GetUniqueId(&id));
   memset(id128, 0, OFFTB_UNIQUE_ID_BYTES);
   memcpy(id128, &id, sizeof(id));
   return 0;
@@ -68,7 +70,9 @@ int offtb_world_init(int rank, int size, int device, const void *id128) {
     if (!id128) { set_error("a unique id is required for size > 1"); return -1; }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    OFFTB_NCCL(ncclCommInitRank(&w.nccl, size, id, rank));
+    const NcclApi *nc = nccl_api();
+    if (!nc) return -1;
+    OFFTB_NCCL(nc->CommInitRank(&w.nccl, size, id, rank));
   }
   w.up = true; w.local = false; w.size = size; w.rank = rank; w.device = device;
   return 0;
@@ -106,7 +110,7 @@ int offtb_world_barrier(void) {
   if (w.nccl) {
     static int *flag = nullptr;
     if (!flag) OFFTB_CUDA(cudaMalloc(&flag, sizeof(int)));
-    OFFTB_NCCL(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, w.nccl, 0));
+    OFFTB_NCCL(nccl_api()->AllReduce(flag, flag, 1, ncclInt, ncclSum, w.nccl, 0));
     OFFTB_CUDA(cudaStreamSynchronize(0));
   }
   return 0;
@@ -115,7 +119,7 @@ int offtb_world_barrier(void) {
 void offtb_world_fin(void) {
   World &w = world();
   if (!w.up) return;
-  if (w.nccl) { ncclCommDestroy(w.nccl); w.nccl = nullptr; }
+  if (w.nccl) { nccl_api()->CommDestroy(w.nccl); w.nccl = nullptr; }
   w = World();
 }
 

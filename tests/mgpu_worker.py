@@ -1,0 +1,89 @@
+"""One rank of the multi-GPU parity run (launched by torchrun, one process per GPU, NCCL).
+
+Every rank builds the plan through the C API, fills its input box of the seeded global grid,
+runs offt_3d_execute on its own GPU (real grouped ncclSend/ncclRecv exchanges), and rank 0
+gathers all outputs and compares them through ostart/osize/ostride with the oracle.
+Then the backward transform must return N * input.   usage: torchrun ... tests/mgpu_worker.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import offt_b200 as ob  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from gpu_helpers import box_of, gather_input  # noqa: E402
+
+P = ob.P
+
+
+def cases(p):
+    out = [((64, 32, 128), 1, {P.P1: p}, 64), ((64, 32, 128), 1, {P.P1: 1}, 64), ((64, 64, 64), 1, {P.P1: p, P.S: 1, P.T2: 8, P.W2: 3}, 64),
+           ((32, 64, 64), 1, {P.P1: 1, P.S: 1, P.T1: 5, P.W1: 1}, 64), ((256, 256, 256), 1, {P.P1: p, P.S: 1}, 64),
+           ((128, 64, 64), 1, {P.P1: p}, 32)]
+    if p >= 4:
+        out += [((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.RY: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
+    return out
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(ob.get_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ob.world_init(rank, world, local, idt.cpu().numpy().tobytes())
+    orc = O.Oracle()
+    failures = 0
+    for N, oned, custom, bits in cases(world):
+        ob.set_default_precision(bits)
+        cdt = np.complex128 if bits == 64 else np.complex64
+        tol = 1e-12 if bits == 64 else 1e-5
+        grid = O.grid_values(11, *N)
+        plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom=custom)
+        box = box_of(plan, N, world)
+        arr = torch.from_numpy(np.ascontiguousarray(O.scatter_input(box, grid.astype(cdt)))).to(dev)
+        plan.execute(arr)
+        launches = plan.last_launches
+        fwd = arr.cpu().numpy()
+        plan.execute_inverse(arr)
+        back = arr.cpu().numpy()
+        plan.fin()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (box, fwd, back))
+        if rank == 0:
+            boxes = []
+            for b, f, _ in gathered:
+                b.data = f
+                boxes.append(b)
+            got = O.gather_output(boxes, cdt)
+            want = O.gather_output(orc.execute(grid, world, orc.resolve_params(*N, world, custom), oned, 0))
+            e1 = O.rel_l2(got, want)
+            e2 = O.rel_l2(got, np.fft.fftn(grid))
+            rt = gather_input(boxes, [g[2] for g in gathered], cdt) / np.prod(N)
+            e3 = O.rel_l2(rt, grid)
+            ok = e1 < tol and e2 < tol and e3 < tol and launches > 0 and not np.isnan(got).any()
+            failures += 0 if ok else 1
+            print(f"{'ok  ' if ok else 'FAIL'} N={N} p={world} oned={oned} custom={custom} bits={bits}: vs oracle {e1:.2e}  vs numpy {e2:.2e}  "
+                  f"round trip {e3:.2e}  launches/rank {launches}", flush=True)
+    ob.set_default_precision(64)
+    ob.world_fin()
+    ft = torch.tensor([failures], device=dev)
+    dist.broadcast(ft, 0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU PARITY", "PASSED" if failures == 0 else f"FAILED ({failures})", flush=True)
+    sys.exit(int(ft.item()) != 0)
+
+
+if __name__ == "__main__":
+    main()

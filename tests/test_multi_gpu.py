@@ -1,0 +1,23 @@
+"""-m gpu, needs >= 2 GPUs: the one-process-per-GPU path with real NCCL exchanges against the oracle.
+(The driver's 1-GPU box skips it; run with `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`.)"""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+pytestmark = pytest.mark.gpu
+
+
+def test_nccl_ranks_match_oracle():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 8 if n >= 8 else 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", str(ROOT / "tests" / "mgpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0 and "MGPU PARITY PASSED" in res.stdout
