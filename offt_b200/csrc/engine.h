@@ -48,6 +48,11 @@ struct World {
   ncclComm_t nccl = nullptr;
 };
 World &world();
+// Collective over the NCCL world: every rank passes one cudaMalloc'd allocation and gets back the addresses at
+// which all ranks' allocations are mapped in this process (its own pointer for itself), over cudaIpc handles
+// gathered with ncclAllGather.  Returns non-zero (error set) if peer mapping is not possible.
+int world_ipc_share(void *mine, std::vector<void *> &mapped);
+void world_ipc_release(std::vector<void *> &mapped);
 
 // ---- tunables (params.cu) ---------------------------------------------------------------
 std::vector<std::vector<int>> params_grid(int Nx, int Ny, int Nz, int p);
@@ -68,8 +73,22 @@ struct Ring {
   int depth = 0;                 // W + 1
   long long slot_elems = 0;      // complex elements per send (or recv) slot
   std::vector<void *> send, recv;
+  std::vector<long long> send_off, recv_off;   // the same slots as element offsets into the ring chunk
   std::vector<cudaEvent_t> packed, recvd;
+  unsigned long long tiles_done = 0;           // tiles of this phase executed so far (sequence base of the flags)
 };
+
+// Flag words of the fused exchange, one block per rank in an IPC-shared allocation.  Peers write them over NVLink.
+//   arrived[phase][j]  : group member j has stored its block of tile number arrived into my landing slot
+//   released[phase][j] : group member j has finished reading the tile number it stored from/into its slot
+struct XFlags {
+  unsigned arrived[2][OFFTB_MAX_GROUP];
+  unsigned released[2][OFFTB_MAX_GROUP];
+  unsigned done_counter[2];
+  unsigned pad[30];
+};
+
+enum ExchangeMode { XCHG_NCCL, XCHG_FUSED };
 
 struct Engine {
   struct _offt_plan *po = nullptr;
@@ -81,6 +100,10 @@ struct Engine {
   void *d_user = nullptr;        // device copy when the caller passes host memory
   void *d_scratch = nullptr;     // second array for the transposed output layouts
   void *d_ring = nullptr;        // one chunk carved into both phases' rings (they alias, as in the reference)
+  ExchangeMode xmode = XCHG_NCCL;
+  XFlags *d_flags = nullptr;               // this rank's flag block
+  std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
+  std::vector<void *> peer_flags;          // every world rank's flag block as mapped here
   void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz
   Ring ring[2];
   cudaStream_t s_comp = nullptr, s_comm = nullptr, s_user = nullptr;

@@ -36,7 +36,11 @@ static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStre
     env_ctas = e ? atoi(e) : 0;
     // these kernels live on shared memory, not on L1: take the largest shared carve-out
     cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, fft_kernel<T, CFG>);
+    smem_optin -= (int)fa.sharedSizeBytes;   // the kernel's static shared memory counts against the same limit
+    cudaError_t ea = cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (ea != cudaSuccess) { sm_count = 0; return ea; }
   }
   const long long ntiles = nbatch >> args.c_log;
   if (ntiles <= 0) return cudaSuccess;

@@ -58,6 +58,8 @@ struct FftMap {
   unsigned B0, B1;
 };
 
+#define OFFTB_MAX_GROUP 8   // ranks in one exchange group (one NVSwitch box)
+
 struct FftArgs {
   const void *in;
   void *out;
@@ -71,6 +73,19 @@ struct FftArgs {
   // Ry rule of the reference (offt-compute.c:1484, 1708): transform a column only if
   // lo <= (x % 10) < hi, x = ry_x0 + batch digit `ry_level`; ry_level < 0: always
   int ry_level, ry_x0, ry_lo, ry_hi;
+  // Fused exchange (plan.cu): when out_split is set, block a = n >> om.n_lg of the output does not live at
+  // out + a*om.n_hi but in out_tab[a] - the receive slot of peer a, mapped over NVLink (or this rank's own).
+  // Before touching memory every CTA waits until wait_flags[j] >= wait_value for all j < wait_count (peers
+  // have released the slots); the last CTA to finish publishes signal_value to signal_ptrs[0..signal_count).
+  int out_split;
+  void *out_tab[OFFTB_MAX_GROUP];
+  const unsigned *wait_flags;
+  int wait_count;
+  unsigned wait_value;
+  unsigned *signal_ptrs[OFFTB_MAX_GROUP];
+  int signal_count;
+  unsigned signal_value;
+  unsigned *done_counter;   // zeroed device word, returns to zero after the launch
 };
 
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
@@ -183,9 +198,18 @@ __device__ __forceinline__ unsigned digit_b(const FftMap &m, unsigned b, int lev
   return level == 1 ? r % m.B1 : r / m.B1;
 }
 
+// address of output point k of the column whose batch offset is bofs (elements)
+template <typename T>
+__device__ __forceinline__ cx<T> *out_ptr(const FftArgs &a, void *const *s_tab, long long bofs, int k) {
+  const int hi = k >> a.om.n_lg;
+  const long long lo = (long long)(k & ((1 << a.om.n_lg) - 1)) * a.om.n_lo;
+  if (a.out_split) return (cx<T> *)s_tab[hi] + (bofs + lo);
+  return (cx<T> *)a.out + (bofs + (long long)hi * a.om.n_hi + lo);
+}
+
 template <typename T, class CFG, int S>
 __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg, const FftArgs &a, cx<T> *sm,
-                                          cx<T> *__restrict__ gout, unsigned bblock, int t, int s_mul, int s_base, T cj) {
+                                          void *const *s_tab, long long bofs, unsigned bblock, int t, int s_mul, int s_base, T cj) {
   constexpr int N = CFG::N, E = CFG::E, TT = CFG::T, NS = CFG::NS;
   constexpr int R = CFG::radix(S), NU = E / R, P = CFG::P(S), M = CFG::M(S);
 
@@ -222,7 +246,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
       }
     }
     __syncthreads();
-    fft_stage<T, CFG, S + 1>(v, wreg, a, sm, gout, bblock, t, s_mul, s_base, cj);
+    fft_stage<T, CFG, S + 1>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
   } else {
     // ---- last stage: output index beta + (N/R)*k
     if (a.load_cfast == a.store_cfast) {
@@ -233,7 +257,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
         for (int pos = 0; pos < R; ++pos) {
           cx<T> e = v[u * R + pos];
           e.y *= cj;
-          gout[map_n(a.om, beta + (N / R) * brev(pos, R))] = e;
+          *out_ptr<T>(a, s_tab, bofs, beta + (N / R) * brev(pos, R)) = e;
         }
       }
     } else {
@@ -257,7 +281,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
         else { k = flat & (N - 1); cc = flat / N; }
         cx<T> val = sm[cc * (N + 1) + k];
         val.y *= cj;
-        ((cx<T> *)a.out)[map_b(a.om, bblock + cc) + map_n(a.om, k)] = val;
+        *out_ptr<T>(a, s_tab, map_b(a.om, bblock + cc), k) = val;
       }
     }
   }
@@ -290,6 +314,19 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
   const int s_base = a.load_cfast ? c : c * CFG::colsize();
   const T cj = a.conj ? (T)-1 : (T)1;
   const int depth = a.depth;
+
+  __shared__ void *s_tab[OFFTB_MAX_GROUP];
+  if (a.out_split)
+    for (int j = tid; j < OFFTB_MAX_GROUP; j += nthreads) s_tab[j] = a.out_tab[j];
+  if (a.wait_count > 0) {
+    // peers release the slots this launch writes (or fill the ones it reads) with a system-scope store
+    for (int j = tid; j < a.wait_count; j += nthreads) {
+      const volatile unsigned *f = a.wait_flags + j;
+      while ((int)(*f - a.wait_value) < 0) __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  if (a.out_split || a.wait_count > 0) __syncthreads();
 
   constexpr int NW = CFG::twregs(CFG::NS - 1) > 0 ? CFG::twregs(CFG::NS - 1) : 1;
   cx<T> wreg[NW];
@@ -334,7 +371,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
       prefetch(tile + (unsigned)(depth - 1) * gridDim.x, ahead);
     }
     const unsigned bblock = tile << a.c_log;
-    cx<T> *gout = (cx<T> *)a.out + map_b(a.om, bblock + c);
+    const long long bofs = map_b(a.om, bblock + c);
 
     // Ry rule: a tile-uniform choice between transforming and merely moving its columns
     bool transform = true;
@@ -343,7 +380,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
       transform = a.ry_lo <= r && r < a.ry_hi;
     }
     if (transform) {
-      fft_stage<T, CFG, 0>(v, wreg, a, sm, gout, bblock, t, s_mul, s_base, cj);
+      fft_stage<T, CFG, 0>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
     } else {
 #pragma unroll
       for (int u = 0; u < NU0; ++u)
@@ -351,12 +388,25 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
         for (int i = 0; i < R0; ++i) {
           cx<T> e = v[u * R0 + i];
           e.y *= cj;   // undo the conjugation of the load
-          gout[map_n(a.om, t + TT * u + (N / R0) * i)] = e;
+          *out_ptr<T>(a, s_tab, bofs, t + TT * u + (N / R0) * i) = e;
         }
     }
     slot = slot + 1 == depth ? 0 : slot + 1;
   }
   cp_async_wait(0);
+  if (a.signal_count > 0) {
+    // every store of this CTA is ordered before the counter; the last CTA tells the peers
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(a.done_counter, 1u);
+      if (prev + 1 == gridDim.x) {
+        *a.done_counter = 0;
+        __threadfence_system();
+        for (int j = 0; j < a.signal_count; ++j) *(volatile unsigned *)a.signal_ptrs[j] = a.signal_value;
+      }
+    }
+  }
 }
 
 }  // namespace offtb

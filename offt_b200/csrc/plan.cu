@@ -130,6 +130,16 @@ struct Launch {
   long long nbatch;
   bool load_cfast, store_cfast;
   int ry_level = -1, ry_x0 = 0, ry_lo = 0, ry_hi = 10;
+  // fused exchange (filled by fuse_writer / fuse_reader)
+  bool split = false;                 // the slot side of the launch is a table of peers' slots
+  void *tab[OFFTB_MAX_GROUP] = {nullptr};
+  const unsigned *wait_flags = nullptr;
+  int wait_count = 0;
+  unsigned wait_value = 0;
+  unsigned *signal_ptrs[OFFTB_MAX_GROUP] = {nullptr};
+  int signal_count = 0;
+  unsigned signal_value = 0;
+  unsigned *done_counter = nullptr;
 };
 
 cudaEvent_t pool_event(Engine &E) {
@@ -162,6 +172,10 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   a.load_cfast = L.load_cfast; a.store_cfast = L.store_cfast;
   a.conj = inverse ? 1 : 0;
   a.ry_level = L.ry_level; a.ry_x0 = L.ry_x0; a.ry_lo = L.ry_lo; a.ry_hi = L.ry_hi;
+  a.out_split = L.split ? 1 : 0;
+  for (int j = 0; j < OFFTB_MAX_GROUP; ++j) { a.out_tab[j] = L.tab[j]; a.signal_ptrs[j] = L.signal_ptrs[j]; }
+  a.wait_flags = L.wait_flags; a.wait_count = L.wait_count; a.wait_value = L.wait_value;
+  a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done_counter;
   a.c_log = pick_c_log(E, info, L);
   if (a.ry_level >= 0 && a.load_cfast != a.store_cfast) { set_error("internal: Ry rule on a transposing launch"); return -1; }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -328,28 +342,107 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bo
   return 0;
 }
 
+// ---- fused exchange ---------------------------------------------------------------------------
+// The writer launch of a tile (K1/K3 forward, the inverses of K2/K4 backward) stores block a of its output
+// straight into group member a's landing slot - over NVLink for the other GPUs of the box - at block index
+// `me`; the reader launch finds the tile complete in its own landing slot.  Landing = receive slots forward,
+// send slots backward (the backward exchange runs recv -> send, see exchange()).  Flags replace MPI_Wait:
+// tile number s = tiles_done + i + 1 of this phase; a writer waits until every member has released tile
+// s - depth (the previous tenant of the slot) and announces s; a reader waits for s from every member and
+// releases s.  Local worlds need no flags: their launches are already ordered on one stream.
+
+void *landing_slot(Engine &E, void *ring_base, int phase, int slot, bool inverse) {
+  Ring &R = E.ring[phase - 1];
+  const long long off = inverse ? R.send_off[slot] : R.recv_off[slot];
+  return at(ring_base, off, E.esz);
+}
+
+int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, int tile, long long myT, bool inverse) {
+  const Dims d = dims_of(E.po);
+  Ring &R = E.ring[phase - 1];
+  const int slot = tile % R.depth;
+  const long long blk = block_elems(d, phase, myT);
+  std::vector<int> members;
+  int me;
+  group_of(E, phase, members, me);
+  if ((int)members.size() > OFFTB_MAX_GROUP) { set_error("fused exchange: groups of more than %d ranks are not supported", OFFTB_MAX_GROUP); return -1; }
+  World &w = world();
+  L.split = true;
+  for (size_t j = 0; j < members.size(); ++j) {
+    void *base = nullptr;
+    if (w.local) {
+      for (Engine *Q : engs) if (Q->po->rank == members[j]) base = Q->d_ring;
+    } else {
+      base = E.peer_ring[members[j]];
+    }
+    if (!base) { set_error("fused exchange: ring of rank %d is not mapped", members[j]); return -1; }
+    Engine *owner = &E;
+    if (w.local) for (Engine *Q : engs) if (Q->po->rank == members[j]) owner = Q;
+    L.tab[j] = at(landing_slot(*owner, base, phase, slot, inverse), (long long)me * blk, E.esz);
+  }
+  if (!w.local) {
+    const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
+    if (R.tiles_done + (unsigned long long)tile >= (unsigned long long)R.depth) {
+      L.wait_flags = E.d_flags->released[phase - 1];
+      L.wait_count = (int)members.size();
+      L.wait_value = seq - (unsigned)R.depth;
+    }
+    for (size_t j = 0; j < members.size(); ++j)
+      L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][me];
+    L.signal_count = (int)members.size();
+    L.signal_value = seq;
+    L.done_counter = &E.d_flags->done_counter[phase - 1];
+  }
+  return 0;
+}
+
+int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
+  World &w = world();
+  if (w.local) return 0;
+  Ring &R = E.ring[phase - 1];
+  std::vector<int> members;
+  int me;
+  group_of(E, phase, members, me);
+  const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
+  L.wait_flags = E.d_flags->arrived[phase - 1];
+  L.wait_count = (int)members.size();
+  L.wait_value = seq;
+  for (size_t j = 0; j < members.size(); ++j)
+    L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][me];
+  L.signal_count = (int)members.size();
+  L.signal_value = seq;
+  L.done_counter = &E.d_flags->done_counter[phase - 1];
+  return 0;
+}
+
 // ---- phases ---------------------------------------------------------------------------------
 
 struct Bufs { void *U; void *A; };   // caller's array and the array between the phases (U or scratch)
 
-int produce(Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+// `writer`: this launch is the first of its tile (the one that feeds the exchange)
+int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
   const int slot = tile % R.depth;
-  if (phase == 1) return run_launch(E, st, ST_K1, L_k1(d, b.U, R.send[slot], (long long)tile * d.T1, myT), inverse);
-  Launch L = L_k3(d, b.A, R.send[slot], (long long)tile * d.T2, myT);
-  if (E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
-  return run_launch(E, st, ST_K3, L, inverse);
+  const bool fused = E.xmode == XCHG_FUSED;
+  // fused: forward, the kernel scatters into the peers' receive slots; backward, it reads this rank's send slot
+  void *buf = R.send[slot];
+  Launch L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(d, b.A, buf, (long long)tile * d.T2, myT);
+  if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
+  if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
+  return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
 }
 
-int consume(Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
   const int slot = tile % R.depth;
-  if (phase == 2) return run_launch(E, st, ST_K4, L_k4(d, R.recv[slot], b.U, (long long)tile * d.T2, myT), inverse);
-  Launch L = L_k2(d, R.recv[slot], b.A, (long long)tile * d.T1, myT);
-  if (E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
-  return run_launch(E, st, ST_K2, L, inverse);
+  const bool fused = E.xmode == XCHG_FUSED;
+  void *buf = R.recv[slot];
+  Launch L = phase == 2 ? L_k4(d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
+  if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
+  if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
+  return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
 }
 
 // The tile pipeline of offt_3d_execute_phase1/2 (offt-compute.c:3501-3862):
@@ -365,33 +458,37 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   const int blocks = (int)((planes + tiling - 1) / tiling);
   Ring &R0 = E0.ring[phase - 1];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
+  const bool fused = E0.xmode == XCHG_FUSED;
   auto tile_T = [&](int i) { return i == blocks - 1 ? planes - (long long)(blocks - 1) * tiling : (long long)tiling; };
   auto first = [&](Engine &E, const Bufs &b, int i) {
-    return inverse ? consume(E, b, phase, i, tile_T(i), true, sc) : produce(E, b, phase, i, tile_T(i), false, sc);
+    return inverse ? consume(engs, E, b, phase, i, tile_T(i), true, sc) : produce(engs, E, b, phase, i, tile_T(i), false, sc);
   };
   auto second = [&](Engine &E, const Bufs &b, int i) {
-    return inverse ? produce(E, b, phase, i, tile_T(i), true, sc) : consume(E, b, phase, i, tile_T(i), false, sc);
+    return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, sc) : consume(engs, E, b, phase, i, tile_T(i), false, sc);
   };
   for (int i = 0; i < blocks; ++i) {
     const int slot = i % R0.depth;
     for (size_t k = 0; k < engs.size(); ++k)
       if (first(*engs[k], bufs[k], i)) return -1;
-    OFFTB_CUDA(cudaEventRecord(R0.packed[slot], sc));
-    OFFTB_CUDA(cudaStreamWaitEvent(sx, R0.packed[slot], 0));
-    if (exchange(engs, phase, slot, tile_T(i), inverse, sx)) return -1;
-    OFFTB_CUDA(cudaEventRecord(R0.recvd[slot], sx));
+    if (!fused) {
+      OFFTB_CUDA(cudaEventRecord(R0.packed[slot], sc));
+      OFFTB_CUDA(cudaStreamWaitEvent(sx, R0.packed[slot], 0));
+      if (exchange(engs, phase, slot, tile_T(i), inverse, sx)) return -1;
+      OFFTB_CUDA(cudaEventRecord(R0.recvd[slot], sx));
+    }
     if (i >= W) {
       const int j = i - W;
-      OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
+      if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
       for (size_t k = 0; k < engs.size(); ++k)
         if (second(*engs[k], bufs[k], j)) return -1;
     }
   }
   for (int j = std::max(blocks - W, 0); j < blocks; ++j) {
-    OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
+    if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
     for (size_t k = 0; k < engs.size(); ++k)
       if (second(*engs[k], bufs[k], j)) return -1;
   }
+  for (Engine *Ep : engs) Ep->ring[phase - 1].tiles_done += (unsigned long long)blocks;
   return 0;
 }
 
@@ -482,10 +579,31 @@ int engine_create(struct _offt_plan *po) {
     for (int s = 0; s < R.depth; ++s) {
       R.send.push_back(slot[ph] ? at(E->d_ring, (2LL * s) * slot[ph], E->esz) : nullptr);
       R.recv.push_back(slot[ph] ? at(E->d_ring, (2LL * s + 1) * slot[ph], E->esz) : nullptr);
+      R.send_off.push_back((2LL * s) * slot[ph]);
+      R.recv_off.push_back((2LL * s + 1) * slot[ph]);
       cudaEvent_t a, b;
       OFFTB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
       OFFTB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
       R.packed.push_back(a); R.recvd.push_back(b);
+    }
+  }
+  // exchange mode: kernels that store into the peers' slots (default), or grouped ncclSend/ncclRecv between
+  // send and receive slots (OFFTB_EXCHANGE=nccl, and whenever peer mapping is not possible)
+  const char *xe = getenv("OFFTB_EXCHANGE");
+  const bool want_fused = !(xe && strcmp(xe, "nccl") == 0) && std::max(c->p1, c->p2) <= OFFTB_MAX_GROUP;
+  if (need > 0 && po->p > 1 && want_fused) {
+    if (w.local) {
+      E->xmode = XCHG_FUSED;
+    } else {
+      OFFTB_CUDA(cudaMalloc((void **)&E->d_flags, sizeof(XFlags)));
+      OFFTB_CUDA(cudaMemset(E->d_flags, 0, sizeof(XFlags)));
+      if (world_ipc_share(E->d_ring, E->peer_ring) == 0 && world_ipc_share(E->d_flags, E->peer_flags) == 0) {
+        E->xmode = XCHG_FUSED;
+      } else {
+        if (!po->rank) fprintf(stderr, "offt_b200: peer mapping unavailable (%s); exchanging with NCCL send/recv\n", last_error());
+        world_ipc_release(E->peer_ring);
+        world_ipc_release(E->peer_flags);
+      }
     }
   }
   po->buffer_chunk = E->d_ring;
@@ -498,6 +616,13 @@ void engine_destroy(struct _offt_plan *po) {
   Engine *E = (Engine *)po->b200;
   if (!E) return;
   cudaDeviceSynchronize();
+  if (!E->peer_ring.empty() || !E->peer_flags.empty()) {
+    // peers may still be storing flags into this rank's memory: leave together (offt_3d_fin is collective)
+    offtb_world_barrier();
+    world_ipc_release(E->peer_ring);
+    world_ipc_release(E->peer_flags);
+  }
+  cudaFree(E->d_flags);
   if (E->registered_host) cudaHostUnregister(E->registered_host);
   for (int a = 0; a < 3; ++a) cudaFree(E->tw[a]);
   cudaFree(E->d_user); cudaFree(E->d_scratch); cudaFree(E->d_ring);

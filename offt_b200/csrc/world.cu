@@ -33,6 +33,59 @@ World &world() {
   return w;
 }
 
+int world_ipc_share(void *mine, std::vector<void *> &mapped) {
+  World &w = world();
+  mapped.assign(w.size, nullptr);
+  if (!w.nccl) { set_error("world_ipc_share needs an NCCL world"); return -1; }
+  const NcclApi *nc = nccl_api();
+  if (!nc) return -1;
+  cudaIpcMemHandle_t h;
+  OFFTB_CUDA(cudaIpcGetMemHandle(&h, mine));
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  unsigned char *d_all = nullptr;
+  OFFTB_CUDA(cudaMalloc(&d_all, hb * (size_t)w.size));
+  OFFTB_CUDA(cudaMemcpy(d_all + hb * (size_t)w.rank, &h, hb, cudaMemcpyHostToDevice));
+  OFFTB_NCCL(nc->AllGather(d_all + hb * (size_t)w.rank, d_all, hb, ncclUint8, w.nccl, 0));
+  OFFTB_CUDA(cudaStreamSynchronize(0));
+  std::vector<cudaIpcMemHandle_t> all(w.size);
+  OFFTB_CUDA(cudaMemcpy(all.data(), d_all, hb * (size_t)w.size, cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  int rc = 0;
+  for (int r = 0; r < w.size; ++r) {
+    if (r == w.rank) { mapped[r] = mine; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+      mapped[r] = nullptr;
+      rc = -1;
+    }
+  }
+  // all ranks must agree whether the mapping worked
+  int *d_ok = nullptr;
+  OFFTB_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+  const int bad = rc ? 1 : 0;
+  OFFTB_CUDA(cudaMemcpy(d_ok, &bad, sizeof(int), cudaMemcpyHostToDevice));
+  OFFTB_NCCL(nc->AllReduce(d_ok, d_ok, 1, ncclInt, ncclSum, w.nccl, 0));
+  OFFTB_CUDA(cudaStreamSynchronize(0));
+  int total = 0;
+  OFFTB_CUDA(cudaMemcpy(&total, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_ok);
+  if (total) {
+    if (!rc) set_error("peer mapping failed on another rank");
+    world_ipc_release(mapped);
+    return -1;
+  }
+  return 0;
+}
+
+void world_ipc_release(std::vector<void *> &mapped) {
+  World &w = world();
+  for (int r = 0; r < (int)mapped.size(); ++r)
+    if (mapped[r] && r != w.rank) cudaIpcCloseMemHandle(mapped[r]);
+  mapped.clear();
+}
+
 }  // namespace offtb
 
 using namespace offtb;
