@@ -84,8 +84,8 @@ struct Ring {
 struct XFlags {
   unsigned arrived[2][OFFTB_MAX_GROUP];
   unsigned released[2][OFFTB_MAX_GROUP];
-  unsigned done_counter[2];
-  unsigned pad[30];
+  unsigned done_counter[2][2];   // [phase][writer, reader]
+  unsigned pad[28];
 };
 
 enum ExchangeMode { XCHG_NCCL, XCHG_FUSED };
@@ -101,6 +101,8 @@ struct Engine {
   void *d_scratch = nullptr;     // second array for the transposed output layouts
   void *d_ring = nullptr;        // one chunk carved into both phases' rings (they alias, as in the reference)
   ExchangeMode xmode = XCHG_NCCL;
+  int grid_cap[2] = {0, 0};                // CTA budgets of writer and reader launches while they overlap
+  FftShape *dry_shape = nullptr;           // run_launch only reports the launch shape
   XFlags *d_flags = nullptr;               // this rank's flag block
   std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
   std::vector<void *> peer_flags;          // every world rank's flag block as mapped here

@@ -19,12 +19,11 @@ namespace offtb {
 // transformed (depth 3) when shared memory allows; the grid is one wave of resident CTAs, each
 // walking its share of the tiles.  OFFTB_DEPTH / OFFTB_CTAS_PER_SM override both for experiments.
 template <typename T, class CFG>
-static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStream_t stream) {
-  FftArgs args = args_in;
+static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
   const int C = 1 << args.c_log;
   const int threads = CFG::T * C;
   const size_t slot = (size_t)C * CFG::colsize() * sizeof(cx<T>);
-  static int sm_count = 0, smem_optin = 0, env_depth = -1, env_ctas = -1;
+  static int sm_count = 0, smem_optin = 0, env_depth = -1, env_ctas = -1, regs = 0;
   if (!sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -38,11 +37,13 @@ static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStre
     cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, fft_kernel<T, CFG>);
+    regs = fa.numRegs;
     smem_optin -= (int)fa.sharedSizeBytes;   // the kernel's static shared memory counts against the same limit
     cudaError_t ea = cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
     if (ea != cudaSuccess) { sm_count = 0; return ea; }
   }
   const long long ntiles = nbatch >> args.c_log;
+  shape->grid = 0;
   if (ntiles <= 0) return cudaSuccess;
   if (ntiles > 2147483647LL) return cudaErrorInvalidConfiguration;
   if (slot > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
@@ -54,7 +55,7 @@ static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStre
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
     if (e != cudaSuccess) return e;
   } else {
-    for (depth = 3; depth >= 1; --depth) {
+    for (depth = args.load_cfast ? 3 : 2; depth >= 1; --depth) {   // contiguous rows: 2 slots measured best
       if (slot * depth > (size_t)smem_optin || (depth > 1 && per_cta < depth)) continue;
       cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
       if (e != cudaSuccess) return e;
@@ -64,10 +65,22 @@ static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStre
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   args.depth = depth;
   args.ntiles = (unsigned)ntiles;
-  const size_t smem = slot * depth;
   if (env_ctas > 0) occ = std::min(occ, env_ctas);
-  const long long grid = std::min<long long>(ntiles, (long long)occ * sm_count);
-  fft_kernel<T, CFG><<<(unsigned)grid, threads, smem, stream>>>(args);
+  long long grid = std::min<long long>(ntiles, (long long)occ * sm_count);
+  if (args.grid_cap > 0) grid = std::min<long long>(grid, args.grid_cap);
+  shape->threads = threads; shape->regs = regs; shape->smem = slot * depth; shape->depth = depth; shape->occ = occ;
+  shape->grid = (unsigned)grid; shape->sm_count = sm_count;
+  return cudaSuccess;
+}
+
+template <typename T, class CFG>
+static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStream_t stream, FftShape *shape_only) {
+  FftArgs args = args_in;
+  FftShape shape;
+  cudaError_t e = plan_one<T, CFG>(args, nbatch, &shape);
+  if (shape_only) *shape_only = shape;
+  if (e != cudaSuccess || shape_only || shape.grid == 0) return e;
+  fft_kernel<T, CFG><<<shape.grid, shape.threads, shape.smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -135,9 +148,9 @@ static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStre
 OFFTB_FFT_CONFIGS(X)
 #undef X
 
-cudaError_t OFFTB_CAT(fft_launch_, OFFTB_INST_N)(int prec, const FftArgs &args, long long nbatch, cudaStream_t stream) {
-  if (prec == PREC_F64) return launch_one<double, CfgD>(args, nbatch, stream);
-  return launch_one<float, CfgF>(args, nbatch, stream);
+cudaError_t OFFTB_CAT(fft_launch_, OFFTB_INST_N)(int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only) {
+  if (prec == PREC_F64) return launch_one<double, CfgD>(args, nbatch, stream, shape_only);
+  return launch_one<float, CfgF>(args, nbatch, stream, shape_only);
 }
 
 void OFFTB_CAT(fft_info_, OFFTB_INST_N)(int prec, FftKernelInfo *info) {

@@ -58,7 +58,7 @@ struct FftMap {
   unsigned B0, B1;
 };
 
-#define OFFTB_MAX_GROUP 8   // ranks in one exchange group (one NVSwitch box)
+#define OFFTB_MAX_GROUP 16   // ranks in one exchange group (one NVSwitch box holds 8)
 
 struct FftArgs {
   const void *in;
@@ -67,6 +67,7 @@ struct FftArgs {
   FftMap im, om;
   int c_log;       // log2(columns per CTA)
   int depth;       // shared-memory ring slots (1: no prefetch)
+  int grid_cap;    // > 0: at most this many CTAs in the grid (launches that share the SMs with another kernel)
   unsigned ntiles; // batch / columns per CTA
   int load_cfast, store_cfast;
   int conj;        // 1: backward transform via conj(FFT(conj(x)))
@@ -198,13 +199,11 @@ __device__ __forceinline__ unsigned digit_b(const FftMap &m, unsigned b, int lev
   return level == 1 ? r % m.B1 : r / m.B1;
 }
 
-// address of output point k of the column whose batch offset is bofs (elements)
+// address of output point k of the column whose batch offset is bofs (elements): block k >> n_lg of the output
+// starts at s_tab[block] - the peers' slots in a fused exchange, out + block*n_hi otherwise
 template <typename T>
 __device__ __forceinline__ cx<T> *out_ptr(const FftArgs &a, void *const *s_tab, long long bofs, int k) {
-  const int hi = k >> a.om.n_lg;
-  const long long lo = (long long)(k & ((1 << a.om.n_lg) - 1)) * a.om.n_lo;
-  if (a.out_split) return (cx<T> *)s_tab[hi] + (bofs + lo);
-  return (cx<T> *)a.out + (bofs + (long long)hi * a.om.n_hi + lo);
+  return (cx<T> *)s_tab[k >> a.om.n_lg] + (bofs + (long long)(k & ((1 << a.om.n_lg) - 1)) * a.om.n_lo);
 }
 
 template <typename T, class CFG, int S>
@@ -316,17 +315,22 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
   const int depth = a.depth;
 
   __shared__ void *s_tab[OFFTB_MAX_GROUP];
-  if (a.out_split)
-    for (int j = tid; j < OFFTB_MAX_GROUP; j += nthreads) s_tab[j] = a.out_tab[j];
+  for (int j = tid; j < OFFTB_MAX_GROUP; j += nthreads)
+    s_tab[j] = a.out_split ? a.out_tab[j] : (void *)((cx<T> *)a.out + (long long)j * a.om.n_hi);
   if (a.wait_count > 0) {
     // peers release the slots this launch writes (or fill the ones it reads) with a system-scope store
     for (int j = tid; j < a.wait_count; j += nthreads) {
       const volatile unsigned *f = a.wait_flags + j;
-      while ((int)(*f - a.wait_value) < 0) __nanosleep(100);
+      const long long t0 = clock64();
+      while ((int)(*f - a.wait_value) < 0) {
+        __nanosleep(100);
+        // a peer that never answers (a rank died, mismatched plans) must not hang the GPU: give up after ~10 s
+        if (clock64() - t0 > 20000000000LL) __trap();
+      }
     }
     __threadfence_system();
   }
-  if (a.out_split || a.wait_count > 0) __syncthreads();
+  __syncthreads();
 
   constexpr int NW = CFG::twregs(CFG::NS - 1) > 0 ? CFG::twregs(CFG::NS - 1) : 1;
   cx<T> wreg[NW];

@@ -8,7 +8,7 @@
 namespace offtb {
 
 #define X(N, ...)                                                                                  \
-  cudaError_t fft_launch_##N(int prec, const FftArgs &args, long long nbatch, cudaStream_t stream); \
+  cudaError_t fft_launch_##N(int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only); \
   void fft_info_##N(int prec, FftKernelInfo *info);
 OFFTB_FFT_CONFIGS(X)
 #undef X
@@ -65,14 +65,22 @@ int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0,
   return lg;
 }
 
-cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream) {
+static cudaError_t dispatch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only) {
   if (nbatch & ((1LL << args.c_log) - 1)) return cudaErrorInvalidValue;
   switch (N) {
-#define X(N, ...) case N: return fft_launch_##N(prec, args, nbatch, stream);
+#define X(N, ...) case N: return fft_launch_##N(prec, args, nbatch, stream, shape_only);
     OFFTB_FFT_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream) {
+  return dispatch(N, prec, args, nbatch, stream, nullptr);
+}
+
+cudaError_t fft_shape(int N, int prec, const FftArgs &args, long long nbatch, FftShape *shape) {
+  return dispatch(N, prec, args, nbatch, nullptr, shape);
 }
 
 }  // namespace offtb

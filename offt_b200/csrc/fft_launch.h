@@ -17,6 +17,13 @@ struct FftKernelInfo {
 // Returns the number of complex entries written (< N); out must hold 2*N long doubles.
 int fft_twiddle_table(int N, int prec, long double *out);
 
+// what one launch occupies: resolved ring depth, grid, and the per-CTA resources
+struct FftShape {
+  int threads = 0, regs = 0, depth = 0, occ = 0, sm_count = 0;
+  size_t smem = 0;
+  unsigned grid = 0;
+};
+
 // Fills `info` for length N; returns false if N is not a supported length.
 bool fft_kernel_info(int N, int prec, FftKernelInfo *info);
 
@@ -26,5 +33,7 @@ int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0,
 // Launches ceil(nbatch / 2^c_log) CTAs.  nbatch must be a multiple of 2^c_log.
 // Returns cudaSuccess or the launch error.
 cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream);
+// the same decisions without launching
+cudaError_t fft_shape(int N, int prec, const FftArgs &args, long long nbatch, FftShape *shape);
 
 }  // namespace offtb

@@ -85,6 +85,10 @@ int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
       set_error("transform length %d: only powers of two from 2 to 8192 are implemented", n);
       return -3;
     }
+  if (p1 > OFFTB_MAX_GROUP || p2 > OFFTB_MAX_GROUP) {
+    set_error("process grid %dx%d: exchange groups of more than %d ranks are not supported", p1, p2, OFFTB_MAX_GROUP);
+    return -5;
+  }
   if (Nx % p1 || Ny % p1 || Ny % p2 || Nz % p2) {
     set_error("grid %dx%dx%d does not divide evenly over %dx%d ranks (uneven splits are not implemented yet)", Nx, Ny, Nz, p1, p2);
     return -4;
@@ -140,6 +144,7 @@ struct Launch {
   int signal_count = 0;
   unsigned signal_value = 0;
   unsigned *done_counter = nullptr;
+  int grid_cap = 0;
 };
 
 cudaEvent_t pool_event(Engine &E) {
@@ -176,8 +181,14 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   for (int j = 0; j < OFFTB_MAX_GROUP; ++j) { a.out_tab[j] = L.tab[j]; a.signal_ptrs[j] = L.signal_ptrs[j]; }
   a.wait_flags = L.wait_flags; a.wait_count = L.wait_count; a.wait_value = L.wait_value;
   a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done_counter;
+  a.grid_cap = L.grid_cap;
   a.c_log = pick_c_log(E, info, L);
   if (a.ry_level >= 0 && a.load_cfast != a.store_cfast) { set_error("internal: Ry rule on a transposing launch"); return -1; }
+  if (E.dry_shape) {
+    cudaError_t se = fft_shape(L.N, E.prec, a, L.nbatch, E.dry_shape);
+    if (se != cudaSuccess) { set_error("kernel shape (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(se)); return -1; }
+    return 0;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
   cudaError_t err = fft_launch(L.N, E.prec, a, L.nbatch, st);
@@ -238,24 +249,39 @@ Launch L_k2(const Dims &d, const void *recv, void *A, long long x0, long long my
   return L;
 }
 
-// K3: FFTy + pack2 (compute_ffty_pack2, offt-compute.c:1636-2345; buffer layout of :1773-1776)
-Launch L_k3(const Dims &d, const void *A, void *send, long long z0, long long myT) {
+// z chunk of the phase-2 slots: the tile's z planes are split z = z_hi*Cz + z_lo and a slot block is laid out
+// [x][z_hi][y_local][z_lo].  One CTA of K3 (Cz columns of z, all y of one x) then writes, per destination, ONE
+// contiguous run of M4*Cz elements with consecutive lanes on consecutive addresses - 512-byte stores that cross
+// NVLink efficiently - instead of 64-byte pieces (the reference's [x][y_local][z] order, offt-compute.c:1773-1776,
+// measured 390 GB/s per direction in the fused exchange).  K4 reads Cz-element rows.  The layout is internal to
+// the ring; what the caller sees (ostride) is unchanged.
+long long z_chunk(const Engine &E, long long myT) {
+  static const long long env_cz = getenv("OFFTB_CZ") ? atoll(getenv("OFFTB_CZ")) : 0;   // experiments
+  long long cz = env_cz > 0 ? env_cz : (E.prec == PREC_F64 ? 4 : 8);
+  while (cz > 1 && myT % cz) cz /= 2;
+  return cz;
+}
+
+// K3: FFTy + pack2 (compute_ffty_pack2, offt-compute.c:1636-2345)
+Launch L_k3(const Engine &E, const Dims &d, const void *A, void *send, long long z0, long long myT) {
   Launch L;
+  const long long cz = z_chunk(E, myT);
   L.N = (int)d.Ny; L.axis = 1; L.in = A; L.out = send;
-  L.im = mk_map(z0, 0, 0, d.dY, myT, 1, d.m1, d.dX, 0);
-  // y splits into (destination, y_local): block a holds [x][y_local][z_tile]
-  L.om = mk_map(0, d.M4, d.M1 * d.M4 * myT, myT, myT, 1, d.m1, myT * d.M4, 0);
+  L.im = mk_map(z0, 0, 0, d.dY, cz, 1, myT / cz, cz, d.dX);
+  // y splits into (destination, y_local): block a holds [x][z_hi][y_local][z_lo]
+  L.om = mk_map(0, d.M4, d.M1 * d.M4 * myT, cz, cz, 1, myT / cz, d.M4 * cz, myT * d.M4);
   L.nbatch = myT * d.m1; L.load_cfast = L.store_cfast = true;
   return L;
 }
 
 // K4: unpack2 + FFTx (compute_unpack2_fftx, offt-compute.c:2347-2993; addresses :2447-2450, 2567-2570, 2684-2687)
-Launch L_k4(const Dims &d, const void *recv, void *U, long long z0, long long myT) {
+Launch L_k4(const Engine &E, const Dims &d, const void *recv, void *U, long long z0, long long myT) {
   Launch L;
+  const long long cz = z_chunk(E, myT);
   L.N = (int)d.Nx; L.axis = 0; L.in = recv; L.out = U;
-  // x splits into (source, x_local): block a holds [x_local][y][z_tile]
-  L.im = mk_map(0, d.M1, d.M1 * d.M4 * myT, myT * d.M4, myT, 1, d.m4, myT, 0);
-  L.om = mk_map(z0 * d.os2, 0, 0, d.os0, myT, d.os2, d.m4, d.os1, 0);
+  // x splits into (source, x_local): block a holds [x_local][z_hi][y][z_lo]; batch digits (z_lo, y, z_hi)
+  L.im = mk_map(0, d.M1, d.M1 * d.M4 * myT, myT * d.M4, cz, 1, d.m4, cz, d.M4 * cz);
+  L.om = mk_map(z0 * d.os2, 0, 0, d.os0, cz, d.os2, d.m4, d.os1, cz * d.os2);
   L.nbatch = myT * d.m4; L.load_cfast = true; L.store_cfast = (d.os2 == 1);
   return L;
 }
@@ -351,6 +377,40 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bo
 // s - depth (the previous tenant of the slot) and announces s; a reader waits for s from every member and
 // releases s.  Local worlds need no flags: their launches are already ordered on one stream.
 
+// Writer and reader launches of a phase can run on two streams, ordered only by the flags, so that the writer's
+// NVLink stores overlap the reader's HBM passes.  A reader that filled the SMs would spin on its flags while the
+// writer it waits for could not start, so both grids are capped: the SMs offer `slots` CTA places that fit either
+// kernel (sized for the larger of the two), the writer gets a share of them and the reader the rest, and whatever
+// the placement the writer always finds room.  Fewer than two places per SM: one stream, launch order.
+// OFFTB_OVERLAP=0 forces one stream; OFFTB_WRITER_SHARE sets the writer's percentage of the places (default 25).
+bool overlap_wanted() {
+  static const int v = getenv("OFFTB_OVERLAP") ? atoi(getenv("OFFTB_OVERLAP")) : 1;
+  return v != 0;
+}
+
+bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
+  E.grid_cap[0] = E.grid_cap[1] = 0;
+  if (!overlap_wanted() || w.grid == 0 || r.grid == 0) return false;
+  int dev = 0, smem_sm = 0, regs_sm = 0, thr_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  const int threads = std::max(w.threads, r.threads);
+  const int regs = (std::max(w.regs, r.regs) + 7) / 8 * 8;
+  const size_t smem = std::max(w.smem, r.smem) + 1024 + 64;   // per-CTA reservation and the kernel's static table
+  const int warps = (threads + 31) / 32;
+  long long per_sm = std::min<long long>({(long long)regs_sm / ((long long)regs * 32 * warps), (long long)(smem_sm / smem),
+                                          (long long)thr_sm / threads, 32LL});
+  if (per_sm < 2) return false;
+  const long long slots = per_sm * w.sm_count;
+  static const int share = getenv("OFFTB_WRITER_SHARE") ? atoi(getenv("OFFTB_WRITER_SHARE")) : 25;
+  long long gw = std::max<long long>(1, std::min<long long>(slots - 1, slots * std::min(std::max(share, 1), 99) / 100));
+  E.grid_cap[0] = (int)gw;
+  E.grid_cap[1] = (int)(slots - gw);
+  return true;
+}
+
 void *landing_slot(Engine &E, void *ring_base, int phase, int slot, bool inverse) {
   Ring &R = E.ring[phase - 1];
   const long long off = inverse ? R.send_off[slot] : R.recv_off[slot];
@@ -391,7 +451,8 @@ int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, in
       L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][me];
     L.signal_count = (int)members.size();
     L.signal_value = seq;
-    L.done_counter = &E.d_flags->done_counter[phase - 1];
+    L.done_counter = &E.d_flags->done_counter[phase - 1][0];
+    L.grid_cap = E.grid_cap[0];
   }
   return 0;
 }
@@ -411,7 +472,8 @@ int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
     L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][me];
   L.signal_count = (int)members.size();
   L.signal_value = seq;
-  L.done_counter = &E.d_flags->done_counter[phase - 1];
+  L.done_counter = &E.d_flags->done_counter[phase - 1][1];
+  L.grid_cap = E.grid_cap[1];
   return 0;
 }
 
@@ -427,8 +489,8 @@ int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   const bool fused = E.xmode == XCHG_FUSED;
   // fused: forward, the kernel scatters into the peers' receive slots; backward, it reads this rank's send slot
   void *buf = R.send[slot];
-  Launch L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(d, b.A, buf, (long long)tile * d.T2, myT);
-  if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
+  Launch L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(E, d, b.A, buf, (long long)tile * d.T2, myT);
+  if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 2; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
   if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
   return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
 }
@@ -439,7 +501,7 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   const int slot = tile % R.depth;
   const bool fused = E.xmode == XCHG_FUSED;
   void *buf = R.recv[slot];
-  Launch L = phase == 2 ? L_k4(d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
+  Launch L = phase == 2 ? L_k4(E, d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
   if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
   if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
   return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
@@ -460,11 +522,33 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
   const bool fused = E0.xmode == XCHG_FUSED;
   auto tile_T = [&](int i) { return i == blocks - 1 ? planes - (long long)(blocks - 1) * tiling : (long long)tiling; };
+  // fused exchange between processes: readers on the second stream, ordered against the writers by flags alone
+  bool two = false;
+  if (fused && !world().local && blocks > 1) {
+    // shapes of tile 0's two launches, without launching
+    FftShape shw, shr;
+    Engine &E = E0;
+    E.grid_cap[0] = E.grid_cap[1] = 0;
+    E.dry_shape = &shw;
+    int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+    E.dry_shape = &shr;
+    if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+    E.dry_shape = nullptr;
+    if (rc) return -1;
+    two = plan_overlap(E, shw, shr);
+  } else {
+    E0.grid_cap[0] = E0.grid_cap[1] = 0;
+  }
+  cudaStream_t s2 = two ? sx : sc;
+  if (two) {
+    OFFTB_CUDA(cudaEventRecord(R0.packed[0], sc));
+    OFFTB_CUDA(cudaStreamWaitEvent(s2, R0.packed[0], 0));
+  }
   auto first = [&](Engine &E, const Bufs &b, int i) {
     return inverse ? consume(engs, E, b, phase, i, tile_T(i), true, sc) : produce(engs, E, b, phase, i, tile_T(i), false, sc);
   };
   auto second = [&](Engine &E, const Bufs &b, int i) {
-    return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, sc) : consume(engs, E, b, phase, i, tile_T(i), false, sc);
+    return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, s2) : consume(engs, E, b, phase, i, tile_T(i), false, s2);
   };
   for (int i = 0; i < blocks; ++i) {
     const int slot = i % R0.depth;
@@ -487,6 +571,10 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
     for (size_t k = 0; k < engs.size(); ++k)
       if (second(*engs[k], bufs[k], j)) return -1;
+  }
+  if (two) {
+    OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
+    OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[0], 0));
   }
   for (Engine *Ep : engs) Ep->ring[phase - 1].tiles_done += (unsigned long long)blocks;
   return 0;

@@ -28,7 +28,7 @@ def cases(p):
            ((32, 64, 64), 1, {P.P1: 1, P.S: 1, P.T1: 5, P.W1: 1}, 64), ((256, 256, 256), 1, {P.P1: p, P.S: 1}, 64),
            ((128, 64, 64), 1, {P.P1: p}, 32)]
     if p >= 4:
-        out += [((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.RY: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
+        out += [((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.Ry: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
     return out
 
 
