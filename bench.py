@@ -196,9 +196,12 @@ def own_arm(args):
         ob.world_init(0, 1, local, None)
 
     P = ob.P
-    custom = {P.P1: world, P.S: args.S}
-    if args.T2 > 0:
-        custom[P.T2] = args.T2
+    # tunables: the reference leaves S, T2, W2 to its tuner; these are the values the sweep in DESIGN.md picked
+    S = args.S if args.S >= 0 else (1 if world == 1 else 0)
+    custom = {P.P1: world, P.S: S}
+    T2 = args.T2 if args.T2 > 0 else (64 if world > 1 and N[2] >= 256 else 0)
+    if T2 > 0:
+        custom[P.T2] = T2
     if args.W2 >= 0:
         custom[P.W2] = args.W2
     plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
@@ -288,9 +291,14 @@ def own_arm(args):
     if world > 1:
         xb = (world - 1) / world * 16 * (N[0] * N[1] * N[2]) / world      # bytes each GPU sends (and receives)
         xms = acc.get("exchange2", 0.0)
+        fused = xms == 0.0     # fused exchange: the NVLink stores are part of the K3 launches, there is no separate copy
+        if fused:
+            xms = acc.get("k3_ffty", 0.0)
         roofline["exchange"] = {"bytes_out_per_gpu": int(xb), "device_ms_sum_of_tiles": round(xms, 4),
+                                "how": "stores of the K3 (FFTy + pack) launches into the peers' slots" if fused else "grouped ncclSend/ncclRecv",
                                 "GBps_per_direction": round(xb / (xms * 1e-3) / 1e9, 1) if xms > 0 else None,
-                                "peak": NVLINK_GBS, "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900"}
+                                "peak": NVLINK_GBS, "frac": round(xb / (xms * 1e-3) / 1e9 / NVLINK_GBS, 4) if xms > 0 else None,
+                                "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900"}
 
     # ---- e2e: host arrays through the C API (H2D + transform + D2H inside the timed region)
     e2e = None
@@ -364,7 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--grid", default="", help="NxMxL or N (default: 512^3 at 1 GPU, 1024^3 otherwise)")
-    ap.add_argument("--S", type=int, default=1, help="tunable _S_: 1 = x-y-z output, no transposes (the reference's STRIDE mode); 0 = z-y-x")
+    ap.add_argument("--S", type=int, default=-1, help="tunable _S_: 1 = x-y-z output (the reference's STRIDE mode); 0 = z-y-x (its default); -1: 1 on one GPU, 0 on several")
     ap.add_argument("--T2", type=int, default=0, help="tile thickness of the exchange phase (0: reference default)")
     ap.add_argument("--W2", type=int, default=-1, help="overlap window (-1: reference default)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture (profiles/)")

@@ -1,0 +1,65 @@
+"""-m gpu: the reference's own driver, run-fft.c, compiled UNMODIFIED against include/offt.h and linked to the
+B200 library (offt_b200/dropin/Makefile), run the way job-test.sh:13 runs it.  Its `-v` spot print - the only
+"is the answer right" check the reference has (run-fft.c:452-503) - must show the closed-form DFT of the init()
+ramp, i.e. the same four numbers the unmodified reference printed over the shims (tests/test_oracle.py)."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+EXE = ROOT / "offt_b200" / "dropin" / "run-fft"
+pytestmark = pytest.mark.gpu
+
+
+def _printed(out):
+    vals = []
+    for line in out.splitlines():
+        m = re.match(r"p 0: 0 0 (\d): (\S+) (\S+)", line)
+        if m:
+            vals.append(complex(float(m.group(2)), float(m.group(3))))
+    return vals
+
+
+def _want(N):
+    return [N ** 3 * (N - 1) / 2 * 111 + 0j] + [N ** 3 / (np.exp(-2j * np.pi * k / N) - 1) for k in (1, 2, 3)]
+
+
+def _need_exe():
+    if not EXE.exists():
+        pytest.fail(f"{EXE} is not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists)")
+
+
+@pytest.mark.parametrize("flags", [[], ["-S", "1"]])
+def test_run_fft_single_rank(flags):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    _need_exe()
+    N = 64
+    res = subprocess.run([str(EXE), "-N", str(N), "-n", str(N), "-L", str(N), "-r", "2", "-m", "1", "-v", "-a", "0"] + flags,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    got = _printed(res.stdout)
+    assert len(got) == 4, res.stdout[-2000:]
+    np.testing.assert_allclose(got, _want(N), rtol=1e-9, atol=1e-3)   # the driver prints 5 decimals
+    assert "t_min" in res.stdout
+
+
+def test_run_fft_ranks_over_offtrun():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    _need_exe()
+    p = 4 if n >= 4 else 2
+    N = 128
+    cmd = [str(ROOT / "offt_b200" / "bin" / "offtrun"), "-n", str(p), str(EXE), "-N", str(N), "-n", str(N), "-L", str(N),
+           "-r", "3", "-m", "1", "-v", "-a", "0", "-o", "-d", str(p)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    got = _printed(res.stdout)
+    assert len(got) == 4, res.stdout[-2000:]
+    np.testing.assert_allclose(got, _want(N), rtol=1e-9, atol=1e-2)
