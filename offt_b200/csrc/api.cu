@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine.h"
 
@@ -114,12 +115,34 @@ struct _offt_plan *offt_3d_init(int Nx, int Ny, int Nz, double *in, double *out,
   return po;
 }
 
+// The reference driver reads po->comm->ostride for its -v print AFTER offt_3d_fin (run-fft.c:421 vs :477-478),
+// which only works there because freed heap blocks keep their tail.  The plan, its parameters and its layout
+// descriptor (a few hundred bytes) therefore stay readable until the world is torn down (MPI_Finalize).
+static std::vector<struct _offt_plan *> &graveyard() {
+  static std::vector<struct _offt_plan *> g;
+  return g;
+}
+
+void offtb_release_finished_plans(void) {
+  for (struct _offt_plan *po : graveyard()) {
+    offt_comm_free(po->comm);
+    free(po->params);
+    free(po);
+  }
+  graveyard().clear();
+}
+
 void offt_3d_fin(struct _offt_plan *po) {
   if (!po) return;
   engine_destroy(po);
-  offt_comm_free(po->comm);
-  free(po->params);
-  free(po);
+  graveyard().push_back(po);
+  if (graveyard().size() > 64) {   // long-lived processes that create many plans: keep only the recent ones
+    struct _offt_plan *old = graveyard().front();
+    graveyard().erase(graveyard().begin());
+    offt_comm_free(old->comm);
+    free(old->params);
+    free(old);
+  }
 }
 
 static int execute_one(struct _offt_plan *po, double *in, double *out, bool inverse) {
@@ -138,7 +161,16 @@ static int execute_one(struct _offt_plan *po, double *in, double *out, bool inve
 
 void offt_3d_execute(struct _offt_plan *po, double *in, double *out, int is_tuning) {
   (void)is_tuning;
+  static const bool dbg = getenv("OFFTB_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "offt_3d_execute(%p, %p, %p): before\n", (void *)po, (void *)in, (void *)out);
   if (execute_one(po, in, out, false)) fatal_or_return("offt_3d_execute");
+  if (dbg) {
+    cudaPointerAttributes attr;
+    const bool host = cudaPointerGetAttributes(&attr, out) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (host) fprintf(stderr, "offt_3d_execute: after, out[0..3] = %g %g %g %g, %d launches, %.3f ms\n", out[0], out[1], out[2], out[3],
+                      eng(po)->launches, eng(po)->last_ms);
+  }
 }
 
 int offt_3d_execute_inverse(struct _offt_plan *po, double *in, double *out) {

@@ -418,10 +418,15 @@ void *landing_slot(Engine &E, void *ring_base, int phase, int slot, bool inverse
   return at(ring_base, off, E.esz);
 }
 
+// slot of a tile: by its running number over all executes of the plan, so that the tenant before it in the slot
+// is always the tile `depth` numbers earlier - the one the flags make the writer wait for - also when the tiles
+// of one execute are not a multiple of the depth
+int slot_of(const Ring &R, int tile) { return (int)((R.tiles_done + (unsigned long long)tile) % (unsigned long long)R.depth); }
+
 int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, int tile, long long myT, bool inverse) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
-  const int slot = tile % R.depth;
+  const int slot = slot_of(R, tile);
   const long long blk = block_elems(d, phase, myT);
   std::vector<int> members;
   int me;
@@ -486,7 +491,7 @@ struct Bufs { void *U; void *A; };   // caller's array and the array between the
 int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
-  const int slot = tile % R.depth;
+  const int slot = slot_of(R, tile);
   const bool fused = E.xmode == XCHG_FUSED;
   // fused: forward, the kernel scatters into the peers' receive slots; backward, it reads this rank's send slot
   void *buf = R.send[slot];
@@ -499,7 +504,7 @@ int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
 int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
-  const int slot = tile % R.depth;
+  const int slot = slot_of(R, tile);
   const bool fused = E.xmode == XCHG_FUSED;
   void *buf = R.recv[slot];
   Launch L = phase == 2 ? L_k4(E, d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
@@ -552,7 +557,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, s2) : consume(engs, E, b, phase, i, tile_T(i), false, s2);
   };
   for (int i = 0; i < blocks; ++i) {
-    const int slot = i % R0.depth;
+    const int slot = slot_of(R0, i);
     for (size_t k = 0; k < engs.size(); ++k)
       if (first(*engs[k], bufs[k], i)) return -1;
     if (!fused) {
@@ -563,13 +568,13 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     }
     if (i >= W) {
       const int j = i - W;
-      if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
+      if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
       for (size_t k = 0; k < engs.size(); ++k)
         if (second(*engs[k], bufs[k], j)) return -1;
     }
   }
   for (int j = std::max(blocks - W, 0); j < blocks; ++j) {
-    if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[j % R0.depth], 0));
+    if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
     for (size_t k = 0; k < engs.size(); ++k)
       if (second(*engs[k], bufs[k], j)) return -1;
   }
@@ -660,16 +665,21 @@ int engine_create(struct _offt_plan *po) {
   const bool use2 = E->sched == SCHED_PENCIL || E->sched == SCHED_SLAB_PX1;
   long long slot[2] = {use1 ? (long long)d.T1 * d.M2 * d.M3 * d.p2 : 0, use2 ? d.M1 * d.M4 * d.p1 * (long long)d.T2 : 0};
   int depth[2] = {d.W1 + 1, d.W2 + 1};
-  const long long need = std::max(2 * slot[0] * depth[0], 2 * slot[1] * depth[1]);
+  // The reference lets the two phases share one chunk (set_buffer_chunk, offt-compute.c:684-710).  Here the phases
+  // get disjoint parts: in the fused exchange a rank that has entered phase 2 stores into its peers' phase-2 slots
+  // while a slower peer may still be reading its phase-1 slots, and only same-phase slots are guarded by flags.
+  const long long part[2] = {2 * slot[0] * depth[0], 2 * slot[1] * depth[1]};
+  const long long base[2] = {0, part[0]};
+  const long long need = part[0] + part[1];
   if (need > 0) OFFTB_CUDA(cudaMalloc(&E->d_ring, (size_t)need * E->esz));
   for (int ph = 0; ph < 2; ++ph) {
     Ring &R = E->ring[ph];
     R.depth = depth[ph]; R.slot_elems = slot[ph];
     for (int s = 0; s < R.depth; ++s) {
-      R.send.push_back(slot[ph] ? at(E->d_ring, (2LL * s) * slot[ph], E->esz) : nullptr);
-      R.recv.push_back(slot[ph] ? at(E->d_ring, (2LL * s + 1) * slot[ph], E->esz) : nullptr);
-      R.send_off.push_back((2LL * s) * slot[ph]);
-      R.recv_off.push_back((2LL * s + 1) * slot[ph]);
+      R.send.push_back(slot[ph] ? at(E->d_ring, base[ph] + (2LL * s) * slot[ph], E->esz) : nullptr);
+      R.recv.push_back(slot[ph] ? at(E->d_ring, base[ph] + (2LL * s + 1) * slot[ph], E->esz) : nullptr);
+      R.send_off.push_back(base[ph] + (2LL * s) * slot[ph]);
+      R.recv_off.push_back(base[ph] + (2LL * s + 1) * slot[ph]);
       cudaEvent_t a, b;
       OFFTB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
       OFFTB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));

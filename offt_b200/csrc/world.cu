@@ -169,8 +169,11 @@ int offtb_world_barrier(void) {
   return 0;
 }
 
+void offtb_release_finished_plans(void);
+
 void offtb_world_fin(void) {
   World &w = world();
+  offtb_release_finished_plans();
   if (!w.up) return;
   if (w.nccl) { nccl_api()->CommDestroy(w.nccl); w.nccl = nullptr; }
   w = World();
