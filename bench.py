@@ -168,6 +168,17 @@ def config_of(args, N):
             "l2": "arrays (>= 2 GiB per GPU) are larger than the 126 MB L2 and are re-filled from a pristine copy between steps"}
 
 
+def traffic_of(N, kernel, args):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or null"""
+    if args.traffic is not None:
+        return args.traffic
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())["bytes_per_launch"]
+        return t.get(f"{N[0]}x{N[1]}x{N[2]}:{kernel}")
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 # ------------------------------------------------------------------------------------ own arm
 def own_arm(args):
     import numpy as np
@@ -287,7 +298,7 @@ def own_arm(args):
                 "frac": round(achieved / peak, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(pass_bytes / passes[dom]["launches_per_step"]),
                 "avg_launch_ms": round(passes[dom]["ms_per_step"] / passes[dom]["launches_per_step"], 5),
-                "traffic": args.traffic, "passes": passes}
+                "traffic": traffic_of(N, dom, args), "passes": passes}
     if world > 1:
         xb = (world - 1) / world * 16 * (N[0] * N[1] * N[2]) / world      # bytes each GPU sends (and receives)
         xms = acc.get("exchange2", 0.0)

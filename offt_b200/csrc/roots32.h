@@ -1,4 +1,4 @@
-// generated by the snippet recorded in DESIGN.md (roots of unity exp(-2*pi*i*k/32), 25 significant digits)
+// roots of unity exp(-2*pi*i*k/32), 25 significant digits; tools/check_roots32.py re-derives and checks every entry
 #pragma once
 namespace offtb {
 template <int K32> struct Root32;
