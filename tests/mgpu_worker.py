@@ -75,7 +75,34 @@ def main():
             failures += 0 if ok else 1
             print(f"{'ok  ' if ok else 'FAIL'} N={N} p={world} oned={oned} custom={custom} bits={bits}: vs oracle {e1:.2e}  vs numpy {e2:.2e}  "
                   f"round trip {e3:.2e}  launches/rank {launches}", flush=True)
+    # the tuning loop (ah_tuning's fetch -> measure -> report, offt-tuning.c:879-1006) on the device: the plan must
+    # come back with a feasible point on the reference's grid, identical on every rank, and still transform correctly
     ob.set_default_precision(64)
+    N, oned, custom = (128, 64, 128), 1, {P.P1: world}
+    grid = O.grid_values(3, *N)
+    plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom=custom)
+    box = box_of(plan, N, world)
+    arr = torch.from_numpy(np.ascontiguousarray(O.scatter_input(box, grid))).to(dev)
+    trials = plan.tune(arr, 8)
+    tuned = plan.params
+    arr.copy_(torch.from_numpy(np.ascontiguousarray(O.scatter_input(box, grid))))
+    plan.execute(arr)
+    fwd = arr.cpu().numpy()
+    plan.fin()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (box, fwd, tuned))
+    if rank == 0:
+        boxes = []
+        for b, f, _ in gathered:
+            b.data = f
+            boxes.append(b)
+        same = all(g[2] == tuned for g in gathered)
+        rng = ob.params_range(*N, world)
+        on_grid = all(tuned[k] in rng[k] for k in (P.T1, P.W1, P.T2, P.W2))
+        e = O.rel_l2(O.gather_output(boxes), np.fft.fftn(grid))
+        ok = same and on_grid and e < 1e-12 and trials >= 1
+        failures += 0 if ok else 1
+        print(f"{'ok  ' if ok else 'FAIL'} tuning: {trials} trials -> T2 {tuned[P.T2]} W2 {tuned[P.W2]}, same on all ranks {same}, on grid {on_grid}, vs numpy {e:.2e}", flush=True)
     ob.world_fin()
     ft = torch.tensor([failures], device=dev)
     dist.broadcast(ft, 0)
