@@ -399,7 +399,7 @@ bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
   cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
   const int threads = std::max(w.threads, r.threads);
   const int regs = (std::max(w.regs, r.regs) + 7) / 8 * 8;
-  const size_t smem = std::max(w.smem, r.smem) + 1024 + 64;   // per-CTA reservation and the kernel's static table
+  const size_t smem = std::max(w.smem, r.smem) + 1024 + 256;   // per-CTA reservation and the kernel's static shared memory
   const int warps = (threads + 31) / 32;
   long long per_sm = std::min<long long>({(long long)regs_sm / ((long long)regs * 32 * warps), (long long)(smem_sm / smem),
                                           (long long)thr_sm / threads, 32LL});
