@@ -213,8 +213,9 @@ def own_arm(args):
     T2 = args.T2 if args.T2 > 0 else (64 if world > 1 and N[2] >= 256 else 0)
     if T2 > 0:
         custom[P.T2] = T2
-    if args.W2 >= 0:
-        custom[P.W2] = args.W2
+    W2 = args.W2 if args.W2 >= 0 else (3 if world > 1 and N[2] >= 256 else -1)   # profiles/r01_cfg3_sweep_1024_8gpu.json
+    if W2 >= 0:
+        custom[P.W2] = W2
     plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
     alloc = plan.alloc_elems
     nbytes = alloc * 16

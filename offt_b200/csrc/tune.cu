@@ -31,6 +31,20 @@ double agree_max(double x) {
   return x;
 }
 
+// The CPU cache sub-tile sizes and MPI_Test frequencies are accepted and ignored by this implementation, but the
+// reference's feasibility rules tie them to T (e.g. Pz2 <= T2, offt-tuning.c:178-205): a search that moves T would
+// be blocked by knobs that do nothing here.  Pull them into range instead (the same spirit as ADJUST_POINT,
+// offt-tuning.c:90-118), so that feasibility is decided by P1, T and W alone.
+void repair_ignored(int Nx, int Ny, int Nz, int p, int *v) {
+  const int p1 = v[_P1_] > 0 ? v[_P1_] : 1, p2 = p / p1 > 0 ? p / p1 : 1;
+  auto cd = [](int a, int b) { return (a + b - 1) / b; };
+  const int M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(Nz, p2), M4 = cd(Ny, p1);
+  auto clamp = [&](int i, int hi) { v[i] = std::max(1, std::min(v[i], std::max(hi, 1))); };
+  clamp(_Px1_, v[_T1_]); clamp(_Py1_, M2); clamp(_Ux1_, v[_T1_]); clamp(_Uz1_, M3);
+  clamp(_Px2_, M1); clamp(_Pz2_, v[_T2_]); clamp(_Uy2_, M4); clamp(_Uz2_, v[_T2_]);
+  for (int i : {_Fz_, _FP1_, _FU1_, _Fy1_, _Fy2_, _FP2_, _FU2_, _Fx_}) v[i] = 0;
+}
+
 bool rebuild(struct _offt_plan *po, const int *v) {
   engine_destroy(po);
   memcpy(po->params->v, v, sizeof(int) * PARAM_COUNT);
@@ -53,11 +67,13 @@ extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int ma
   const auto grid = params_grid(Nx, Ny, Nz, p);
   std::vector<int> best(po->params->v, po->params->v + PARAM_COUNT);
   params_adjust(Nx, Ny, Nz, p, po->is_oned, best.data());
+  repair_ignored(Nx, Ny, Nz, p, best.data());
   std::map<std::vector<int>, double> database;   // the reference's tmp-db file, kept in memory
   int evaluated = 0;
 
   auto measure = [&](std::vector<int> v) -> double {
     params_adjust(Nx, Ny, Nz, p, po->is_oned, v.data());
+    repair_ignored(Nx, Ny, Nz, p, v.data());
     int bad;
     // the ring-size rule of the reference is about MPI_Alloc_mem on its clusters; HBM has room
     // for far larger rings, so only the structural rules decide here
@@ -107,6 +123,7 @@ extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int ma
     }
   }
   params_adjust(Nx, Ny, Nz, p, po->is_oned, best.data());
+  repair_ignored(Nx, Ny, Nz, p, best.data());
   if (!rebuild(po, best.data())) return -1;
   po->params->is_converged = 1;
   if (verbose) { printf("@ BEST %.6f ", best_t); print_params(po->params->v); }
