@@ -381,7 +381,10 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bo
 // NVLink stores overlap the reader's HBM passes.  A reader that filled the SMs would spin on its flags while the
 // writer it waits for could not start, so both grids are capped: the SMs offer `slots` CTA places that fit either
 // kernel (sized for the larger of the two), the writer gets a share of them and the reader the rest, and whatever
-// the placement the writer always finds room.  Fewer than two places per SM: one stream, launch order.
+// the placement the writer always finds room.  Fewer than two places per SM (2048-point strided tiles take
+// 131 KB and the whole register file): one stream, launch order - splitting the SMs between the two kernels
+// instead was measured and loses, because the rate of remote stores scales with the number of SMs issuing
+// them (2 GPUs, 64x2048x2048: 4.33 ms on one stream, 7.56 / 5.40 ms with 25 % / 40 % of the SMs for the writer).
 // OFFTB_OVERLAP=0 forces one stream; OFFTB_WRITER_SHARE sets the writer's percentage of the places (default 50:
 // 1024^3 on 8 GPUs 4.39 ms at 50, 4.58 at 30, 5.24 on one stream).
 bool overlap_wanted() {
