@@ -50,6 +50,27 @@ def workload_for(args):
     return (512, 512, 512) if args.gpus == 1 else (1024, 1024, 1024)
 
 
+class c_stdout_to_stderr:
+    """the library prints the reference's parameter lines on stdout (print_params, offt-compute.c:3416, 3469);
+    this program's stdout carries exactly one JSON line, so those go to stderr while plans are built or torn down"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except OSError:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs"""
@@ -216,7 +237,8 @@ def own_arm(args):
     W2 = args.W2 if args.W2 >= 0 else (3 if world > 1 and N[2] >= 256 else -1)   # profiles/r01_cfg3_sweep_1024_8gpu.json
     if W2 >= 0:
         custom[P.W2] = W2
-    plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
+    with c_stdout_to_stderr():
+        plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
     alloc = plan.alloc_elems
     nbytes = alloc * 16
     # seeded synthetic grid, generated on the device per rank (local box of a global random grid)
