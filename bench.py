@@ -50,25 +50,26 @@ def workload_for(args):
     return (512, 512, 512) if args.gpus == 1 else (1024, 1024, 1024)
 
 
-class c_stdout_to_stderr:
-    """the library prints the reference's parameter lines on stdout (print_params, offt-compute.c:3416, 3469);
-    this program's stdout carries exactly one JSON line, so those go to stderr while plans are built or torn down"""
+# This program's stdout carries exactly ONE JSON line.  Libraries underneath print there too (the reference's
+# parameter lines from print_params, offt-compute.c:3416, 3469; NCCL's version banner), so file descriptor 1 is
+# pointed at stderr for the whole run and the line goes out through the saved descriptor.
+_REAL_STDOUT = None
 
-    def __enter__(self):
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
         sys.stdout.flush()
-        self.saved = os.dup(1)
+        _REAL_STDOUT = os.dup(1)
         os.dup2(2, 1)
-        return self
 
-    def __exit__(self, *exc):
-        try:
-            import ctypes
-            ctypes.CDLL(None).fflush(None)
-        except OSError:
-            pass
-        os.dup2(self.saved, 1)
-        os.close(self.saved)
-        return False
+
+def emit(line: str):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -174,7 +175,7 @@ def reference_arm(args):
                              "host_cores_visible": cores,
                              "note": "reference pipeline (offt-compute.c, unmodified) over the stand-in MPI and FFT of oracle/shim, not FFTW"},
             "e2e": {"value": round(val, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -209,6 +210,7 @@ def own_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
+    quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,8 +239,7 @@ def own_arm(args):
     W2 = args.W2 if args.W2 >= 0 else (3 if world > 1 and N[2] >= 256 else -1)   # profiles/r01_cfg3_sweep_1024_8gpu.json
     if W2 >= 0:
         custom[P.W2] = W2
-    with c_stdout_to_stderr():
-        plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
+    plan = ob.Plan(*N, is_oned=1 if world > 1 else 0, is_notest=1, custom=custom)
     alloc = plan.alloc_elems
     nbytes = alloc * 16
     # seeded synthetic grid, generated on the device per rank (local box of a global random grid)
@@ -395,7 +396,7 @@ def own_arm(args):
             "parseval_rel_err": parseval, "clocks": clock_rec, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
     if parseval > 1e-9:
         line["invalid"] = f"Parseval check failed ({parseval:.3e})"
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0 if parseval <= 1e-9 else 1
 
 
