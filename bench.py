@@ -82,6 +82,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -96,6 +97,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -106,7 +110,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
+        for line in self.lines[self.first:] or self.lines[-1:]:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -260,12 +264,13 @@ def own_arm(args):
         plan.execute(work)            # synchronous; device time first->last kernel in plan.last_ms
         return plan.last_ms, plan.last_launches
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()            # nvidia-smi needs a few hundred ms to come up: start it before the warm-up
+    for _ in range(max(args.warmup, 3)):
+        one_step()
     barrier()
+    clocks.mark()                 # only samples taken from here on (timed steps + per-kernel timing) are reported
     wall0 = time.perf_counter()
     times, launches = [], 0
     for _ in range(args.steps):
