@@ -23,10 +23,11 @@ static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
   const int C = 1 << args.c_log;
   const int threads = CFG::T * C;
   const size_t slot = (size_t)C * CFG::colsize() * sizeof(cx<T>);
-  static int sm_count = 0, smem_optin = 0, env_depth = -1, env_ctas = -1, regs = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int sm_count = 0, smem_optin = 0, env_depth = -1, env_ctas = -1, regs = 0, cfg_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!sm_count || dev != cfg_dev) {   // function attributes are per device
+    cfg_dev = dev;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const char *e = getenv("OFFTB_DEPTH");

@@ -1,0 +1,52 @@
+"""CPU: the parts of bench.py's contract that need no GPU - the reference arm prints exactly one JSON line with the
+keys the driver reads, on a small grid; and the product never reaches for the oracle."""
+import json
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "ref_dump").exists(), reason="oracle/_ref/ref_dump not built")
+def test_reference_arm_prints_one_json_line():
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1",
+                          "--grid", "64"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under offt_b200/ or include/ may import, link or execute it"""
+    offenders = []
+    for path in list((ROOT / "offt_b200").rglob("*")) + list((ROOT / "include").rglob("*")):
+        if path.is_file() and path.suffix in {".py", ".cu", ".cuh", ".h", ".c", ".cpp"} or path.name in {"Makefile", "offtrun"}:
+            text = path.read_text(errors="ignore")
+            if re.search(r"\boracle\b", text, flags=re.I) and "oracle" in text.lower():
+                for n, line in enumerate(text.splitlines(), 1):
+                    code = line.strip()
+                    if code.startswith(("//", "#!", "# ", "*", "/*")):
+                        continue   # prose
+                    if re.search(r"(^\s*(import|from)\s+\S*oracle|#\s*include.*oracle|dlopen\(.*oracle|CDLL\(.*oracle|-loracle|oracle/)", line, flags=re.I):
+                        offenders.append(f"{path.relative_to(ROOT)}:{n}: {line.strip()}")
+    assert not offenders, offenders
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode != 0
+    assert "no CUDA device" in (res.stderr + res.stdout)
+    assert not res.stdout.strip().startswith("{")
