@@ -1,0 +1,133 @@
+// Internal declarations shared by the host-side translation units.
+#pragma once
+#ifndef OFFT_NO_MINMAX
+#define OFFT_NO_MINMAX
+#endif
+#include <cuda_runtime.h>
+#include "nccl_dyn.h"
+
+#include <string>
+#include <vector>
+
+#include "fft_launch.h"
+#include "offt.h"
+#include "offt_b200.h"
+
+namespace offtb {
+
+// ---- errors ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+const char *last_error();
+// what the reference does on a fatal condition (printf + exit(-1), offt-compute.c:3440-3443);
+// bindings that want a return code instead call offtb_set_exit_on_error(0)
+extern int g_exit_on_error;
+void fatal_or_return(const char *where);
+
+#define OFFTB_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      offtb::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+#define OFFTB_NCCL(call)                                                                   \
+  do {                                                                                     \
+    ncclResult_t r__ = (call);                                                             \
+    if (r__ != ncclSuccess) {                                                              \
+      offtb::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, offtb::nccl_api()->GetErrorString(r__)); \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+// ---- world ----------------------------------------------------------------------------
+struct World {
+  bool up = false;
+  bool local = false;   // all ranks emulated in this process on one device
+  int size = 1, rank = 0, device = 0;
+  ncclComm_t nccl = nullptr;
+};
+World &world();
+// Collective over the NCCL world: every rank passes one cudaMalloc'd allocation and gets back the addresses at
+// which all ranks' allocations are mapped in this process (its own pointer for itself), over cudaIpc handles
+// gathered with ncclAllGather.  Returns non-zero (error set) if peer mapping is not possible.
+int world_ipc_share(void *mine, std::vector<void *> &mapped);
+void world_ipc_release(std::vector<void *> &mapped);
+
+// ---- tunables (params.cu) ---------------------------------------------------------------
+std::vector<std::vector<int>> params_grid(int Nx, int Ny, int Nz, int p);
+void params_default(int Nx, int Ny, int Nz, int p, int is_W0, int is_notest, int *v);
+int params_infeasible(int Nx, int Ny, int Nz, int p, const int *v, int *bad);
+void params_adjust(int Nx, int Ny, int Nz, int p, int is_oned, int *v);
+const char *param_name(int i);
+
+// ---- layout (plan.cu) ---------------------------------------------------------------------
+void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy);
+long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1);
+int check_supported(int Nx, int Ny, int Nz, int p, int p1);
+
+enum Schedule { SCHED_SINGLE, SCHED_SLAB_1XP, SCHED_SLAB_PX1, SCHED_PENCIL };
+enum StageId { ST_K1, ST_K2, ST_K3, ST_K4, ST_X1, ST_X2, ST_H2D, ST_D2H, ST_COUNT };
+
+struct Ring {
+  int depth = 0;                 // W + 1
+  long long slot_elems = 0;      // complex elements per send (or recv) slot
+  std::vector<void *> send, recv;
+  std::vector<long long> send_off, recv_off;   // the same slots as element offsets into the ring chunk
+  std::vector<cudaEvent_t> packed, recvd;
+  unsigned long long tiles_done = 0;           // tiles of this phase executed so far (sequence base of the flags)
+};
+
+// Flag words of the fused exchange, one block per rank in an IPC-shared allocation.  Peers write them over NVLink.
+//   arrived[phase][row][j]  : group member j has stored its block of tile number `arrived` into my landing slot
+//   released[phase][row][j] : group member j has finished reading tile number `released` out of its own slot
+// row = ring slot % OFFTB_MAX_RING, so that tiles which complete out of order never share a word
+#define OFFTB_MAX_PHASE_TILES 4096   // tiles one phase launch can count completions for
+
+struct XFlags {
+  unsigned arrived[2][OFFTB_MAX_RING][OFFTB_MAX_GROUP];
+  unsigned released[2][OFFTB_MAX_RING][OFFTB_MAX_GROUP];
+  unsigned done[2][2][OFFTB_MAX_PHASE_TILES];   // [phase][writer, reader][tile of the launch]: items completed
+};
+
+enum ExchangeMode { XCHG_NCCL, XCHG_FUSED };
+
+struct Engine {
+  struct _offt_plan *po = nullptr;
+  int prec = PREC_F64;
+  size_t esz = 16;               // bytes per complex element
+  Schedule sched = SCHED_SINGLE;
+  int rank_x = 0, rank_y = 0;
+  long long alloc = 0;           // complex elements of the caller's array
+  void *d_user = nullptr;        // device copy when the caller passes host memory
+  void *d_scratch = nullptr;     // second array for the transposed output layouts
+  void *d_ring = nullptr;        // one chunk carved into both phases' rings (they alias, as in the reference)
+  ExchangeMode xmode = XCHG_NCCL;
+  int grid_cap[2] = {0, 0};                // CTA budgets of writer and reader launches while they overlap
+  FftShape *dry_shape = nullptr;           // run_launch only reports the launch shape
+  XFlags *d_flags = nullptr;               // this rank's flag block
+  std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
+  std::vector<void *> peer_flags;          // every world rank's flag block as mapped here
+  void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz
+  Ring ring[2];
+  cudaStream_t s_comp = nullptr, s_comm = nullptr, s_user = nullptr;
+  bool async = false;
+  bool stage_timing = false;
+  void *registered_host = nullptr;
+  size_t registered_bytes = 0;
+  int launches = 0;
+  double last_ms = 0.0;
+  double stage_ms[ST_COUNT] = {0};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;  // (stage, begin/end)
+  std::vector<cudaEvent_t> event_pool;
+  size_t event_next = 0;
+};
+
+int engine_create(struct _offt_plan *po);
+void engine_destroy(struct _offt_plan *po);
+// runs the schedule for every plan of `group` (one plan per process in NCCL worlds, all ranks
+// in local worlds); arrays are the callers' in-place arrays (host or device)
+int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *> &arrays, bool inverse);
+
+}  // namespace offtb

@@ -1,0 +1,41 @@
+// Host-side entry to the batched 1-D FFT kernels (fft_kernels.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "fft_kernels.cuh"
+
+namespace offtb {
+
+enum Precision { PREC_F64 = 64, PREC_F32 = 32 };
+
+struct FftKernelInfo {
+  int N, E, T, colsize, maxt;   // colsize: shared-memory elements per column
+  int ns, radix[4];             // stage count and radices
+};
+
+// Host copy of the kernel's twiddle tables for length N (interleaved re, im in long double):
+// for every stage s but the last, M_s entries exp(-2*pi*i*n'/(R_s*M_s)), concatenated.
+// Returns the number of complex entries written (< N); out must hold 2*N long doubles.
+int fft_twiddle_table(int N, int prec, long double *out);
+
+// what one launch occupies: resolved ring depth, grid, and the per-CTA resources
+struct FftShape {
+  int threads = 0, regs = 0, depth = 0, occ = 0, sm_count = 0;
+  size_t smem = 0;
+  unsigned grid = 0;
+};
+
+// Fills `info` for length N; returns false if N is not a supported length.
+bool fft_kernel_info(int N, int prec, FftKernelInfo *info);
+
+// log2 of the columns one CTA transforms (see fft_launch.cu)
+int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long n_stride_elems);
+
+// Launches ceil(nbatch / 2^c_log) CTAs.  nbatch must be a multiple of 2^c_log.
+// Returns cudaSuccess or the launch error.
+cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream);
+// one grid for phase_tiles tiles of nbatch columns each (PhaseArgs, fft_kernels.cuh)
+cudaError_t fft_launch_phase(int N, int prec, const FftArgs &args, const PhaseArgs &ph, long long nbatch, cudaStream_t stream);
+// the same decisions without launching
+cudaError_t fft_shape(int N, int prec, const FftArgs &args, long long nbatch, FftShape *shape);
+
+}  // namespace offtb

@@ -1,0 +1,915 @@
+// Plan construction and the execute schedules of the B200 3-D FFT.
+//
+// What the reference does per rank (offt-compute.c:3864-4048):
+//     [FFTz + pack1] -> all-to-all in the row group -> [unpack1 + FFTy]      (phase 1, x tiles)
+//     mid transpose
+//     [FFTy + pack2] -> all-to-all in the column group -> [unpack2 + FFTx]   (phase 2, z tiles)
+// with tile i's exchange overlapping the compute of tiles i-W .. i+W.
+//
+// Here every bracket is ONE launch of the batched 1-D kernel (fft_kernels.cuh) whose load and
+// store maps do the (un)packing; z stays the contiguous axis of every intermediate array, so
+// no transpose pass exists and the output layout the caller asked for (_S_, is_equalxy,
+// offt-compute.c:282-313) is produced by the store map of the last launch.  Exchanges run on
+// a second stream as grouped ncclSend/ncclRecv between ring slots (depth W+1); cudaEvents
+// replace MPI_Wait (offt-compute.c:3607-3679, 3789-3861).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+namespace offtb {
+
+// ------------------------------------------------------------------------------ layout
+
+namespace {
+
+struct Share { int ceil, floor, extra, mine, start; };
+
+// the last `extra` owners of a split hold one item more (offt-compute.c:141-144, 246-247)
+Share share_of(int N, int owners, int r) {
+  Share s;
+  s.floor = N / owners;
+  s.extra = N % owners;
+  s.ceil = s.floor + (s.extra ? 1 : 0);
+  const int small = owners - s.extra;
+  s.mine = r < small ? s.floor : s.floor + 1;
+  s.start = r < small ? r * s.floor : small * s.floor + (r - small) * (s.floor + 1);
+  return s;
+}
+
+bool is_pow2(long long n) { return n > 0 && (n & (n - 1)) == 0; }
+int lg2(long long n) { int l = 0; while ((1LL << l) < n) ++l; return l; }
+
+}  // namespace
+
+void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy) {
+  const int p2 = p / p1;
+  const int rx = rank / p2, ry = rank % p2;   // rank -> (row, column) of the process grid
+  const Share x1 = share_of(Nx, p1, rx), y2 = share_of(Ny, p2, ry), z2 = share_of(Nz, p2, ry), y1 = share_of(Ny, p1, rx);
+  c->p1 = p1; c->p2 = p2;
+  c->comm1 = c->comm2 = nullptr; c->group1 = c->group2 = nullptr;
+  c->M1 = x1.ceil; c->M2 = y2.ceil; c->M3 = z2.ceil; c->M4 = y1.ceil;
+  c->F1 = x1.floor; c->F2 = y2.floor; c->F3 = z2.floor; c->F4 = y1.floor;
+  c->m1 = x1.mine; c->m2 = y2.mine; c->m3 = z2.mine; c->m4 = y1.mine;
+  c->b1 = x1.extra; c->b2 = y2.extra; c->b3 = z2.extra; c->b4 = y1.extra;
+  // input box: x-y-z, z contiguous, rows padded so that both phases fit the same array
+  c->istart[0] = x1.start; c->istart[1] = y2.start; c->istart[2] = 0;
+  c->isize[0] = x1.mine; c->isize[1] = y2.mine; c->isize[2] = Nz;
+  const int yrows = std::max(c->M2 * p2, c->M4 * p1);
+  c->istride[0] = yrows * c->M3; c->istride[1] = c->M3 * p2; c->istride[2] = 1;
+  // output box: all of x, this rank's y block of the column split and z block of the row split
+  c->ostart[0] = 0; c->ostart[1] = y1.start; c->ostart[2] = z2.start;
+  c->osize[0] = Nx; c->osize[1] = y1.mine; c->osize[2] = z2.mine;
+  const int xrow = c->M1 * p1;
+  if (S) { c->ostride[0] = c->M3 * c->M4; c->ostride[1] = c->M3; c->ostride[2] = 1; }                      // x-y-z
+  else if (is_equalxy && c->M1 == c->M4) { c->ostride[0] = 1; c->ostride[1] = xrow * c->M3; c->ostride[2] = xrow; }  // y-z-x
+  else { c->ostride[0] = 1; c->ostride[1] = xrow; c->ostride[2] = xrow * c->M4; }                          // z-y-x
+}
+
+long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1) {
+  const int p2 = p / p1;
+  auto cd = [](long long a, long long b) { return (a + b - 1) / b; };
+  const long long M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(Nz, p2), M4 = cd(Ny, p1);
+  return std::max(M2 * p2, M4 * p1) * M1 * M3;
+}
+
+int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
+  if (p < 1 || p1 < 1 || p % p1 != 0) { set_error("process grid %d = %d x ? is not a grid", p, p1); return -2; }
+  const int p2 = p / p1;
+  FftKernelInfo info;
+  for (int n : {Nx, Ny, Nz})
+    if (!is_pow2(n) || !fft_kernel_info(n, PREC_F64, &info)) {
+      set_error("transform length %d: only powers of two from 2 to 8192 are implemented", n);
+      return -3;
+    }
+  if (p1 > OFFTB_MAX_GROUP || p2 > OFFTB_MAX_GROUP) {
+    set_error("process grid %dx%d: exchange groups of more than %d ranks are not supported", p1, p2, OFFTB_MAX_GROUP);
+    return -5;
+  }
+  if (Nx % p1 || Ny % p1 || Ny % p2 || Nz % p2) {
+    set_error("grid %dx%dx%d does not divide evenly over %dx%d ranks (uneven splits are not implemented yet)", Nx, Ny, Nz, p1, p2);
+    return -4;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ engine
+
+namespace {
+
+int make_twiddles(int N, int prec, void **dev) {
+  std::vector<long double> tab(2 * (size_t)N + 2);
+  const int count = fft_twiddle_table(N, prec, tab.data());
+  if (count < 0) { set_error("no kernel for length %d", N); return -1; }
+  const size_t n = (size_t)std::max(count, 1);
+  std::vector<double> hd(2 * n);
+  std::vector<float> hf(2 * n);
+  for (size_t j = 0; j < 2 * (size_t)count; ++j) { hd[j] = (double)tab[j]; hf[j] = (float)tab[j]; }
+  const size_t bytes = n * (prec == PREC_F64 ? 16 : 8);
+  OFFTB_CUDA(cudaMalloc(dev, bytes));
+  OFFTB_CUDA(cudaMemcpy(*dev, prec == PREC_F64 ? (void *)hd.data() : (void *)hf.data(), bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+FftMap mk_map(long long off, long long nlo_count, long long n_hi, long long n_lo, long long B0, long long s0,
+              long long B1, long long s1, long long s2) {
+  FftMap m;
+  m.off = off;
+  m.n_lg = nlo_count > 0 ? lg2(nlo_count) : 30;   // 30: no split, n_hi unused
+  m.n_hi = n_hi; m.n_lo = n_lo;
+  m.B0 = (unsigned)std::max<long long>(B0, 1); m.B1 = (unsigned)std::max<long long>(B1, 1);
+  m.s0 = s0; m.s1 = s1; m.s2 = s2;
+  return m;
+}
+
+struct Launch {
+  int N;
+  int axis;          // 0 x, 1 y, 2 z -> twiddle table
+  const void *in;
+  void *out;
+  FftMap im, om;
+  long long nbatch;
+  bool load_cfast, store_cfast;
+  int ry_level = -1, ry_x0 = 0, ry_lo = 0, ry_hi = 10;
+  // fused exchange (filled by fuse_writer / fuse_reader)
+  bool split = false;                 // the slot side of the launch is a table of peers' slots
+  void *tab[OFFTB_MAX_RING][OFFTB_MAX_GROUP] = {{nullptr}};
+  const unsigned *wait_flags = nullptr;
+  int wait_count = 0;
+  unsigned wait_value = 0;
+  bool wait_at_load = false;
+  unsigned *signal_ptrs[OFFTB_MAX_GROUP] = {nullptr};
+  int signal_count = 0;
+  unsigned signal_value = 0;
+  int flag_stride = 0;
+  unsigned *done = nullptr;
+  int grid_cap = 0;
+  // phase launch (run_phase_launch): several tiles of a phase in one grid
+  int phase_tiles = 1, ring_depth = 1, slot0 = 0;
+  long long in_step = 0, out_step = 0;
+  int ry_step = 0;
+  const void *in_slot[OFFTB_MAX_RING] = {nullptr};
+};
+
+// what run_launch does to a launch of the backward transform: the same kernel runs the maps the other way round
+void orient(Launch &L, bool inverse) {
+  if (!inverse) return;
+  std::swap(L.im, L.om);
+  std::swap(L.load_cfast, L.store_cfast);
+  const void *t = L.in; L.in = L.out; L.out = const_cast<void *>(t);
+}
+
+cudaEvent_t pool_event(Engine &E) {
+  if (E.event_next == E.event_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    E.event_pool.push_back(ev);
+  }
+  return E.event_pool[E.event_next++];
+}
+
+int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
+  return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, std::max(L.im.n_lo, L.om.n_lo));
+}
+
+int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse, bool oriented = false) {
+  if (L.nbatch <= 0) return 0;
+  FftKernelInfo info;
+  if (!fft_kernel_info(L.N, E.prec, &info)) { set_error("no kernel for length %d", L.N); return -1; }
+  if (L.nbatch * (long long)L.phase_tiles >= (1LL << 32)) { set_error("batch of %lld rows exceeds the 32-bit batch index", L.nbatch * L.phase_tiles); return -1; }
+  FftArgs a;
+  memset(&a, 0, sizeof(a));
+  if (!oriented) orient(L, inverse);
+  a.in = L.in; a.out = L.out; a.tw = E.tw[L.axis];
+  a.im = L.im; a.om = L.om;
+  a.load_cfast = L.load_cfast; a.store_cfast = L.store_cfast;
+  a.conj = inverse ? 1 : 0;
+  a.ry_level = L.ry_level; a.ry_x0 = L.ry_x0; a.ry_lo = L.ry_lo; a.ry_hi = L.ry_hi;
+  a.out_split = L.split ? 1 : 0;
+  for (int j = 0; j < OFFTB_MAX_GROUP; ++j) { a.out_tab[j] = L.tab[0][j]; a.signal_ptrs[j] = L.signal_ptrs[j]; }
+  a.wait_flags = L.wait_flags; a.wait_count = L.wait_count; a.wait_value = L.wait_value;
+  a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done;
+  const bool phased = L.phase_tiles > 1;
+  PhaseArgs ph;
+  memset(&ph, 0, sizeof(ph));
+  if (phased) {
+    ph.phase_tiles = L.phase_tiles; ph.ring_depth = L.ring_depth; ph.slot0 = L.slot0; ph.ry_step = L.ry_step;
+    ph.flag_stride = L.flag_stride; ph.wait_at_load = L.wait_at_load ? 1 : 0;
+    ph.in_step = L.in_step; ph.out_step = L.out_step; ph.done = L.done;
+    for (int r = 0; r < OFFTB_MAX_RING; ++r) {
+      ph.in_slot[r] = L.in_slot[r];
+      for (int j = 0; j < OFFTB_MAX_GROUP; ++j) ph.tab[r][j] = L.tab[r][j];
+    }
+  }
+  a.grid_cap = L.grid_cap;
+  a.c_log = pick_c_log(E, info, L);
+  if (a.ry_level >= 0 && a.load_cfast != a.store_cfast) { set_error("internal: Ry rule on a transposing launch"); return -1; }
+  if (E.dry_shape) {
+    cudaError_t se = fft_shape(L.N, E.prec, a, L.nbatch, E.dry_shape);
+    if (se != cudaSuccess) { set_error("kernel shape (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(se)); return -1; }
+    return 0;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
+  cudaError_t err = phased ? fft_launch_phase(L.N, E.prec, a, ph, L.nbatch, st) : fft_launch(L.N, E.prec, a, L.nbatch, st);
+  if (err != cudaSuccess) { set_error("kernel launch (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(err)); return -1; }
+  if (E.stage_timing) { cudaEventRecord(e1, st); E.timed.push_back({stage, {e0, e1}}); }
+  E.launches++;
+  return 0;
+}
+
+struct Dims {
+  long long Nx, Ny, Nz, p1, p2, M1, M2, M3, M4, m1, m2, m3, m4, isx, isy, dX, dY, os0, os1, os2;
+  int T1, T2, W1, W2, Ry, S;
+};
+
+Dims dims_of(const struct _offt_plan *po) {
+  const struct _offt_comm *c = po->comm;
+  Dims d;
+  d.Nx = po->Nx; d.Ny = po->Ny; d.Nz = po->Nz; d.p1 = c->p1; d.p2 = c->p2;
+  d.M1 = c->M1; d.M2 = c->M2; d.M3 = c->M3; d.M4 = c->M4;
+  d.m1 = c->m1; d.m2 = c->m2; d.m3 = c->m3; d.m4 = c->m4;
+  d.isx = c->istride[0]; d.isy = c->istride[1];
+  d.dY = d.M3; d.dX = d.M3 * d.M4 * d.p1;           // the x-y-z_local array between the phases
+  d.os0 = c->ostride[0]; d.os1 = c->ostride[1]; d.os2 = c->ostride[2];
+  const int *v = po->params->v;
+  d.T1 = v[_T1_]; d.T2 = v[_T2_]; d.W1 = v[_W1_]; d.W2 = v[_W2_]; d.Ry = v[_Ry_]; d.S = v[_S_];
+  return d;
+}
+
+inline char *at(void *base, long long elems, size_t esz) { return (char *)base + (size_t)elems * esz; }
+
+// ---- the launches -----------------------------------------------------------------------
+
+// FFTz over x planes [x0, x0+nx) of the input box, rows contiguous
+Launch L_fftz_local(const Dims &d, const void *in, void *out, long long x0, long long nx) {
+  Launch L;
+  L.N = (int)d.Nz; L.axis = 2; L.in = in; L.out = out;
+  L.im = L.om = mk_map(x0 * d.isx, 0, 0, 1, d.m2, d.isy, nx, d.isx, 0);
+  L.nbatch = d.m2 * nx; L.load_cfast = L.store_cfast = false;
+  return L;
+}
+
+// K1: FFTz + pack1 (reference compute_fftz_pack1, offt-compute.c:905-1206, buffer layout of :1015-1032)
+Launch L_k1(const Dims &d, const void *U, void *send, long long x0, long long myT) {
+  Launch L = L_fftz_local(d, U, send, x0, myT);
+  // z splits into (destination, z_local): block a at a*myT*M2*M3, inside it [x][y][z_local]
+  L.om = mk_map(0, d.M3, myT * d.M2 * d.M3, 1, d.m2, d.M3, myT, d.M2 * d.M3, 0);
+  return L;
+}
+
+// K2: unpack1 + FFTy (compute_unpack1_ffty, offt-compute.c:1208-1520; addresses of :1307-1311)
+Launch L_k2(const Dims &d, const void *recv, void *A, long long x0, long long myT) {
+  Launch L;
+  L.N = (int)d.Ny; L.axis = 1; L.in = recv; L.out = A;
+  // y splits into (source, y_local): block a holds [x][y_local][z]
+  L.im = mk_map(0, d.M2, myT * d.M2 * d.M3, d.M3, d.m3, 1, myT, d.M2 * d.M3, 0);
+  L.om = mk_map(x0 * d.dX, 0, 0, d.dY, d.m3, 1, myT, d.dX, 0);
+  L.nbatch = d.m3 * myT; L.load_cfast = L.store_cfast = true;
+  return L;
+}
+
+// z chunk of the phase-2 slots: the tile's z planes are split z = z_hi*Cz + z_lo and a slot block is laid out
+// [x][z_hi][y_local][z_lo].  One CTA of K3 (Cz columns of z, all y of one x) then writes, per destination, ONE
+// contiguous run of M4*Cz elements with consecutive lanes on consecutive addresses - 512-byte stores that cross
+// NVLink efficiently - instead of 64-byte pieces (the reference's [x][y_local][z] order, offt-compute.c:1773-1776,
+// measured 390 GB/s per direction in the fused exchange).  K4 reads Cz-element rows.  The layout is internal to
+// the ring; what the caller sees (ostride) is unchanged.
+long long z_chunk(const Engine &E, long long myT) {
+  static const long long env_cz = getenv("OFFTB_CZ") ? atoll(getenv("OFFTB_CZ")) : 0;   // experiments
+  long long cz = env_cz > 0 ? env_cz : (E.prec == PREC_F64 ? 4 : 8);
+  while (cz > 1 && myT % cz) cz /= 2;
+  return cz;
+}
+
+// K3: FFTy + pack2 (compute_ffty_pack2, offt-compute.c:1636-2345)
+Launch L_k3(const Engine &E, const Dims &d, const void *A, void *send, long long z0, long long myT) {
+  Launch L;
+  const long long cz = z_chunk(E, myT);
+  L.N = (int)d.Ny; L.axis = 1; L.in = A; L.out = send;
+  L.im = mk_map(z0, 0, 0, d.dY, cz, 1, myT / cz, cz, d.dX);
+  // y splits into (destination, y_local): block a holds [x][z_hi][y_local][z_lo]
+  L.om = mk_map(0, d.M4, d.M1 * d.M4 * myT, cz, cz, 1, myT / cz, d.M4 * cz, myT * d.M4);
+  L.nbatch = myT * d.m1; L.load_cfast = L.store_cfast = true;
+  return L;
+}
+
+// K4: unpack2 + FFTx (compute_unpack2_fftx, offt-compute.c:2347-2993; addresses :2447-2450, 2567-2570, 2684-2687)
+Launch L_k4(const Engine &E, const Dims &d, const void *recv, void *U, long long z0, long long myT) {
+  Launch L;
+  const long long cz = z_chunk(E, myT);
+  L.N = (int)d.Nx; L.axis = 0; L.in = recv; L.out = U;
+  // x splits into (source, x_local): block a holds [x_local][z_hi][y][z_lo]; batch digits (z_lo, y, z_hi)
+  L.im = mk_map(0, d.M1, d.M1 * d.M4 * myT, myT * d.M4, cz, 1, d.m4, cz, d.M4 * cz);
+  L.om = mk_map(z0 * d.os2, 0, 0, d.os0, cz, d.os2, d.m4, d.os1, cz * d.os2);
+  L.nbatch = myT * d.m4; L.load_cfast = true; L.store_cfast = (d.os2 == 1);
+  return L;
+}
+
+// whole-array FFTy in the x-y-z_local array (single rank)
+Launch L_ffty_local(const Dims &d, void *A) {
+  Launch L;
+  L.N = (int)d.Ny; L.axis = 1; L.in = A; L.out = A;
+  L.im = L.om = mk_map(0, 0, 0, d.dY, d.m3, 1, d.m1, d.dX, 0);
+  L.nbatch = d.m3 * d.m1; L.load_cfast = L.store_cfast = true;
+  return L;
+}
+
+// whole-array FFTx from the x-y-z_local array into the output layout (slab 1 x p tail,
+// offt-compute.c:3913-3949, and the single-rank case)
+Launch L_fftx_local(const Dims &d, const void *A, void *U) {
+  Launch L;
+  L.N = (int)d.Nx; L.axis = 0; L.in = A; L.out = U;
+  L.im = mk_map(0, 0, 0, d.dX, d.m3, 1, d.Ny, d.dY, 0);
+  L.om = mk_map(0, 0, 0, d.os0, d.m3, d.os2, d.Ny, d.os1, 0);
+  L.nbatch = d.m3 * d.Ny; L.load_cfast = true; L.store_cfast = (d.os2 == 1);
+  return L;
+}
+
+// ---- exchanges ----------------------------------------------------------------------------
+
+// members of this plan's row (phase 1) or column (phase 2) group and its own index in it
+// (comm1 / comm2 of the reference, offt-compute.c:78-125)
+void group_of(const Engine &E, int phase, std::vector<int> &members, int &me) {
+  const struct _offt_comm *c = E.po->comm;
+  members.clear();
+  if (phase == 1) { for (int j = 0; j < c->p2; ++j) members.push_back(E.rank_x * c->p2 + j); me = E.rank_y; }
+  else { for (int i = 0; i < c->p1; ++i) members.push_back(i * c->p2 + E.rank_y); me = E.rank_x; }
+}
+
+long long block_elems(const Dims &d, int phase, long long myT) {
+  return phase == 1 ? myT * d.M2 * d.M3 : d.M1 * d.M4 * myT;   // offt-compute.c:3523, 3704
+}
+
+// One tile's all-to-all.  `from`/`to` are ring slots: forward sends `send` -> peers' `recv`,
+// the backward transform runs the same exchange from `recv` to `send`.
+int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bool inverse, cudaStream_t st) {
+  World &w = world();
+  for (Engine *Ep : engs) {
+    Engine &E = *Ep;
+    const Dims d = dims_of(E.po);
+    const long long blk = block_elems(d, phase, myT);
+    std::vector<int> members;
+    int me;
+    group_of(E, phase, members, me);
+    Ring &R = E.ring[phase - 1];
+    char *src = (char *)(inverse ? R.recv[slot] : R.send[slot]);
+    char *dst = (char *)(inverse ? R.send[slot] : R.recv[slot]);
+    const size_t bytes = (size_t)blk * E.esz;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
+    if (w.local) {
+      // every emulated rank pulls its blocks out of its peers' slots
+      for (size_t j = 0; j < members.size(); ++j) {
+        Engine *peer = nullptr;
+        for (Engine *Q : engs) if (Q->po->rank == members[j]) peer = Q;
+        if (!peer) { set_error("local world: plan of rank %d missing from the group", members[j]); return -1; }
+        Ring &PR = peer->ring[phase - 1];
+        const char *psrc = (const char *)(inverse ? PR.recv[slot] : PR.send[slot]);
+        OFFTB_CUDA(cudaMemcpyAsync(dst + j * bytes, psrc + (size_t)me * bytes, bytes, cudaMemcpyDeviceToDevice, st));
+      }
+    } else if (members.size() == 1) {
+      OFFTB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      const ncclDataType_t ty = E.prec == PREC_F64 ? ncclDouble : ncclFloat;
+      const NcclApi *nc = nccl_api();
+      if (!nc) return -1;
+      OFFTB_NCCL(nc->GroupStart());
+      for (size_t j = 0; j < members.size(); ++j) {
+        if ((int)j == me) continue;
+        OFFTB_NCCL(nc->Send(src + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
+        OFFTB_NCCL(nc->Recv(dst + j * bytes, (size_t)blk * 2, ty, members[j], w.nccl, st));
+      }
+      OFFTB_NCCL(nc->GroupEnd());
+      OFFTB_CUDA(cudaMemcpyAsync(dst + (size_t)me * bytes, src + (size_t)me * bytes, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (E.stage_timing) { cudaEventRecord(e1, st); E.timed.push_back({phase == 1 ? ST_X1 : ST_X2, {e0, e1}}); }
+  }
+  return 0;
+}
+
+// ---- fused exchange ---------------------------------------------------------------------------
+// The writer launch of a tile (K1/K3 forward, the inverses of K2/K4 backward) stores block a of its output
+// straight into group member a's landing slot - over NVLink for the other GPUs of the box - at block index
+// `me`; the reader launch finds the tile complete in its own landing slot.  Landing = receive slots forward,
+// send slots backward (the backward exchange runs recv -> send, see exchange()).  Flags replace MPI_Wait:
+// tile number s = tiles_done + i + 1 of this phase; a writer waits until every member has released tile
+// s - depth (the previous tenant of the slot) and announces s; a reader waits for s from every member and
+// releases s.  Local worlds need no flags: their launches are already ordered on one stream.
+
+// Writer and reader launches of a phase can run on two streams, ordered only by the flags, so that the writer's
+// NVLink stores overlap the reader's HBM passes.  A reader that filled the SMs would spin on its flags while the
+// writer it waits for could not start, so both grids are capped: the SMs offer `slots` CTA places that fit either
+// kernel (sized for the larger of the two), the writer gets a share of them and the reader the rest, and whatever
+// the placement the writer always finds room.  Fewer than two places per SM (2048-point strided tiles take
+// 131 KB and the whole register file): one stream, launch order - splitting the SMs between the two kernels
+// instead was measured and loses, because the rate of remote stores scales with the number of SMs issuing
+// them (2 GPUs, 64x2048x2048: 4.33 ms on one stream, 7.56 / 5.40 ms with 25 % / 40 % of the SMs for the writer).
+// OFFTB_OVERLAP=0 forces one stream; OFFTB_WRITER_SHARE sets the writer's percentage of the places (default 50:
+// 1024^3 on 8 GPUs 4.39 ms at 50, 4.58 at 30, 5.24 on one stream).
+bool overlap_wanted() {
+  static const int v = getenv("OFFTB_OVERLAP") ? atoi(getenv("OFFTB_OVERLAP")) : 1;
+  return v != 0;
+}
+
+bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
+  E.grid_cap[0] = E.grid_cap[1] = 0;
+  if (!overlap_wanted() || w.grid == 0 || r.grid == 0) return false;
+  int dev = 0, smem_sm = 0, regs_sm = 0, thr_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  const int threads = std::max(w.threads, r.threads);
+  const int regs = (std::max(w.regs, r.regs) + 7) / 8 * 8;
+  const size_t smem = std::max(w.smem, r.smem) + 1024 + 1024;   // per-CTA reservation and the kernel's static shared memory
+  const int warps = (threads + 31) / 32;
+  long long per_sm = std::min<long long>({(long long)regs_sm / ((long long)regs * 32 * warps), (long long)(smem_sm / smem),
+                                          (long long)thr_sm / threads, 32LL});
+  if (per_sm < 2) return false;
+  const long long slots = per_sm * w.sm_count;
+  static const int share = getenv("OFFTB_WRITER_SHARE") ? atoi(getenv("OFFTB_WRITER_SHARE")) : 50;
+  long long gw = std::max<long long>(1, std::min<long long>(slots - 1, slots * std::min(std::max(share, 1), 99) / 100));
+  E.grid_cap[0] = (int)gw;
+  E.grid_cap[1] = (int)(slots - gw);
+  return true;
+}
+
+void *landing_slot(Engine &E, void *ring_base, int phase, int slot, bool inverse) {
+  Ring &R = E.ring[phase - 1];
+  const long long off = inverse ? R.send_off[slot] : R.recv_off[slot];
+  return at(ring_base, off, E.esz);
+}
+
+// slot of a tile: by its running number over all executes of the plan, so that the tenant before it in the slot
+// is always the tile `depth` numbers earlier - the one the flags make the writer wait for - also when the tiles
+// of one execute are not a multiple of the depth
+int slot_of(const Ring &R, int tile) { return (int)((R.tiles_done + (unsigned long long)tile) % (unsigned long long)R.depth); }
+
+// flag row of a ring slot (XFlags holds OFFTB_MAX_RING rows; deeper rings of per-tile launches share rows, which is
+// safe because those launches complete in order)
+int flag_row(int slot) { return slot % OFFTB_MAX_RING; }
+
+int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, int tile, long long myT, bool inverse) {
+  const Dims d = dims_of(E.po);
+  Ring &R = E.ring[phase - 1];
+  const int slot = slot_of(R, tile);
+  const long long blk = block_elems(d, phase, myT);
+  std::vector<int> members;
+  int me;
+  group_of(E, phase, members, me);
+  if ((int)members.size() > OFFTB_MAX_GROUP) { set_error("fused exchange: groups of more than %d ranks are not supported", OFFTB_MAX_GROUP); return -1; }
+  World &w = world();
+  L.split = true;
+  for (size_t j = 0; j < members.size(); ++j) {
+    void *base = nullptr;
+    if (w.local) {
+      for (Engine *Q : engs) if (Q->po->rank == members[j]) base = Q->d_ring;
+    } else {
+      base = E.peer_ring[members[j]];
+    }
+    if (!base) { set_error("fused exchange: ring of rank %d is not mapped", members[j]); return -1; }
+    Engine *owner = &E;
+    if (w.local) for (Engine *Q : engs) if (Q->po->rank == members[j]) owner = Q;
+    L.tab[0][j] = at(landing_slot(*owner, base, phase, slot, inverse), (long long)me * blk, E.esz);
+  }
+  if (!w.local) {
+    const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
+    const int row = flag_row(slot);
+    L.wait_flags = E.d_flags->released[phase - 1][row];
+    L.wait_count = (int)members.size();
+    L.wait_value = seq - (unsigned)R.depth;      // the slot's previous tenant; not positive for the first tiles: no wait
+    L.wait_at_load = false;
+    for (size_t j = 0; j < members.size(); ++j)
+      L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][row][me];
+    L.signal_count = (int)members.size();
+    L.signal_value = seq;
+    L.done = E.d_flags->done[phase - 1][0];
+    L.grid_cap = E.grid_cap[0];
+  }
+  return 0;
+}
+
+int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
+  World &w = world();
+  if (w.local) return 0;
+  Ring &R = E.ring[phase - 1];
+  std::vector<int> members;
+  int me;
+  group_of(E, phase, members, me);
+  const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
+  const int row = flag_row(slot_of(R, tile));
+  L.wait_flags = E.d_flags->arrived[phase - 1][row];
+  L.wait_count = (int)members.size();
+  L.wait_value = seq;
+  L.wait_at_load = true;
+  for (size_t j = 0; j < members.size(); ++j)
+    L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][row][me];
+  L.signal_count = (int)members.size();
+  L.signal_value = seq;
+  L.done = E.d_flags->done[phase - 1][1];
+  L.grid_cap = E.grid_cap[1];
+  return 0;
+}
+
+// ---- phases ---------------------------------------------------------------------------------
+
+struct Bufs { void *U; void *A; };   // caller's array and the array between the phases (U or scratch)
+
+// the launch that packs tile `tile` (K1 / K3; run backward it is the one that reads the exchanged tile)
+int build_produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, Launch &L) {
+  const Dims d = dims_of(E.po);
+  Ring &R = E.ring[phase - 1];
+  const int slot = slot_of(R, tile);
+  const bool fused = E.xmode == XCHG_FUSED;
+  // fused: forward, the kernel scatters into the peers' receive slots; backward, it reads this rank's send slot
+  void *buf = R.send[slot];
+  L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(E, d, b.A, buf, (long long)tile * d.T2, myT);
+  if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 2; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
+  if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
+  return 0;
+}
+
+// the launch that unpacks tile `tile` (K2 / K4; run backward it is the one that feeds the exchange)
+int build_consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, Launch &L) {
+  const Dims d = dims_of(E.po);
+  Ring &R = E.ring[phase - 1];
+  const int slot = slot_of(R, tile);
+  const bool fused = E.xmode == XCHG_FUSED;
+  void *buf = R.recv[slot];
+  L = phase == 2 ? L_k4(E, d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
+  if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
+  if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
+  return 0;
+}
+
+int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+  Launch L;
+  if (build_produce(engs, E, b, phase, tile, myT, inverse, L)) return -1;
+  return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
+}
+
+int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+  Launch L;
+  if (build_consume(engs, E, b, phase, tile, myT, inverse, L)) return -1;
+  return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
+}
+
+// One launch for all tiles of a phase and role: the per-tile launches of `first` (the writers) or `second` (the
+// readers) differ only by offsets that advance linearly with the tile and by the ring slot, so a single grid can
+// walk them (FftArgs::phase_tiles).  Inputs keep streaming across tile boundaries, and the ~16 us a launch plus a
+// flag round trip cost per tile (T2 x W2 sweep) disappear.  Needs the writer and reader grids resident
+// together for the whole phase (plan_overlap), full tiles only, and 2..OFFTB_MAX_RING ring slots.
+int run_phase_launch(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int blocks, long long myT, bool inverse,
+                     bool first, cudaStream_t st) {
+  Ring &R = E.ring[phase - 1];
+  auto build = [&](int tile, Launch &L) {
+    const bool prod = first != inverse;   // forward: writers produce; backward: writers are the inverted consumers
+    const int rc = prod ? build_produce(engs, E, b, phase, tile, myT, inverse, L) : build_consume(engs, E, b, phase, tile, myT, inverse, L);
+    if (!rc) orient(L, inverse);
+    return rc;
+  };
+  Launch P, L1;
+  if (build(0, P) || build(1, L1)) return -1;
+  const bool by_slot = P.in != L1.in;    // the input is a ring slot
+  if ((by_slot && L1.im.off != P.im.off) || (P.split && L1.om.off != P.om.off)) { set_error("internal: phase launch with a moving slot offset"); return -1; }
+  P.phase_tiles = blocks; P.ring_depth = R.depth; P.slot0 = slot_of(R, 0);
+  P.in_step = L1.im.off - P.im.off; P.out_step = L1.om.off - P.om.off; P.ry_step = L1.ry_x0 - P.ry_x0;
+  void *tab0[OFFTB_MAX_GROUP];
+  for (int j = 0; j < OFFTB_MAX_GROUP; ++j) { tab0[j] = P.tab[0][j]; P.tab[0][j] = nullptr; }
+  for (int s = 0; s < R.depth; ++s) {
+    Launch Ls;
+    if (s == 0) Ls = P; else if (build(s, Ls)) return -1;
+    const int slot = slot_of(R, s);
+    if (by_slot) P.in_slot[slot] = Ls.in;
+    if (P.split) for (int j = 0; j < OFFTB_MAX_GROUP; ++j) P.tab[slot][j] = s == 0 ? tab0[j] : Ls.tab[0][j];
+  }
+  // flags: row 0 of the phase, rows advance with the slot; values advance with the tile
+  XFlags *mine = E.d_flags;
+  const unsigned seq0 = (unsigned)(R.tiles_done + 1ULL);
+  std::vector<int> members;
+  int me;
+  group_of(E, phase, members, me);
+  P.flag_stride = OFFTB_MAX_GROUP;
+  P.wait_count = P.signal_count = (int)members.size();
+  P.wait_at_load = !first;
+  P.wait_flags = first ? mine->released[phase - 1][0] : mine->arrived[phase - 1][0];
+  P.wait_value = first ? seq0 - (unsigned)R.depth : seq0;
+  P.signal_value = seq0;
+  for (size_t j = 0; j < members.size(); ++j) {
+    XFlags *peer = (XFlags *)E.peer_flags[members[j]];
+    P.signal_ptrs[j] = first ? &peer->arrived[phase - 1][0][me] : &peer->released[phase - 1][0][me];
+  }
+  P.done = mine->done[phase - 1][first ? 0 : 1];
+  P.grid_cap = E.grid_cap[first ? 0 : 1];
+  const int stage = first != inverse ? (phase == 1 ? ST_K1 : ST_K3) : (phase == 2 ? ST_K4 : ST_K2);
+  return run_launch(E, st, stage, P, inverse, /*oriented=*/true);
+}
+
+// The tile pipeline of offt_3d_execute_phase1/2 (offt-compute.c:3501-3862):
+//   produce(i); [wait(i-W)]; exchange(i); consume(i-W); ... drain the last W tiles.
+// Forward: produce = K1/K3, consume = K2/K4.  Backward: the same loop with the roles and
+// the ring directions swapped (consume's inverse gathers, produce's inverse scatters).
+int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, bool inverse) {
+  Engine &E0 = *engs[0];
+  const Dims d0 = dims_of(E0.po);
+  const long long planes = phase == 1 ? d0.m1 : d0.m3;              // :3529, :3710
+  const int tiling = phase == 1 ? d0.T1 : d0.T2;
+  const int W = phase == 1 ? d0.W1 : d0.W2;
+  const int blocks = (int)((planes + tiling - 1) / tiling);
+  Ring &R0 = E0.ring[phase - 1];
+  cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
+  const bool fused = E0.xmode == XCHG_FUSED;
+  auto tile_T = [&](int i) { return i == blocks - 1 ? planes - (long long)(blocks - 1) * tiling : (long long)tiling; };
+  // fused exchange between processes: readers on the second stream, ordered against the writers by flags alone
+  bool two = false;
+  if (fused && !world().local && blocks > 1) {
+    // shapes of tile 0's two launches, without launching
+    FftShape shw, shr;
+    Engine &E = E0;
+    E.grid_cap[0] = E.grid_cap[1] = 0;
+    E.dry_shape = &shw;
+    int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+    E.dry_shape = &shr;
+    if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+    E.dry_shape = nullptr;
+    if (rc) return -1;
+    two = plan_overlap(E, shw, shr);
+  } else {
+    E0.grid_cap[0] = E0.grid_cap[1] = 0;
+  }
+  cudaStream_t s2 = two ? sx : sc;
+  if (two) {
+    OFFTB_CUDA(cudaEventRecord(R0.packed[0], sc));
+    OFFTB_CUDA(cudaStreamWaitEvent(s2, R0.packed[0], 0));
+  }
+  static const bool phase_launch_on = !(getenv("OFFTB_PHASE_LAUNCH") && atoi(getenv("OFFTB_PHASE_LAUNCH")) == 0);
+  if (two && phase_launch_on && planes % tiling == 0 && R0.depth >= 2 && R0.depth <= OFFTB_MAX_RING && blocks <= OFFTB_MAX_PHASE_TILES) {
+    // one writer grid and one reader grid for the whole phase, ordered by the flags alone
+    if (run_phase_launch(engs, E0, bufs[0], phase, blocks, tiling, inverse, true, sc)) return -1;
+    if (run_phase_launch(engs, E0, bufs[0], phase, blocks, tiling, inverse, false, s2)) return -1;
+    OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
+    OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[0], 0));
+    E0.ring[phase - 1].tiles_done += (unsigned long long)blocks;
+    return 0;
+  }
+  auto first = [&](Engine &E, const Bufs &b, int i) {
+    return inverse ? consume(engs, E, b, phase, i, tile_T(i), true, sc) : produce(engs, E, b, phase, i, tile_T(i), false, sc);
+  };
+  auto second = [&](Engine &E, const Bufs &b, int i) {
+    return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, s2) : consume(engs, E, b, phase, i, tile_T(i), false, s2);
+  };
+  for (int i = 0; i < blocks; ++i) {
+    const int slot = slot_of(R0, i);
+    for (size_t k = 0; k < engs.size(); ++k)
+      if (first(*engs[k], bufs[k], i)) return -1;
+    if (!fused) {
+      OFFTB_CUDA(cudaEventRecord(R0.packed[slot], sc));
+      OFFTB_CUDA(cudaStreamWaitEvent(sx, R0.packed[slot], 0));
+      if (exchange(engs, phase, slot, tile_T(i), inverse, sx)) return -1;
+      OFFTB_CUDA(cudaEventRecord(R0.recvd[slot], sx));
+    }
+    if (i >= W) {
+      const int j = i - W;
+      if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
+      for (size_t k = 0; k < engs.size(); ++k)
+        if (second(*engs[k], bufs[k], j)) return -1;
+    }
+  }
+  for (int j = std::max(blocks - W, 0); j < blocks; ++j) {
+    if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
+    for (size_t k = 0; k < engs.size(); ++k)
+      if (second(*engs[k], bufs[k], j)) return -1;
+  }
+  if (two) {
+    OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
+    OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[0], 0));
+  }
+  for (Engine *Ep : engs) Ep->ring[phase - 1].tiles_done += (unsigned long long)blocks;
+  return 0;
+}
+
+int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inverse) {
+  Engine &E0 = *engs[0];
+  cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp;
+  // the forward schedule as a list of steps; the backward transform walks it in reverse
+  enum Step { STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL, STEP_PHASE1, STEP_PHASE2 };
+  std::vector<Step> steps;
+  switch (E0.sched) {
+    case SCHED_SINGLE: steps = {STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL}; break;
+    case SCHED_SLAB_1XP: steps = {STEP_PHASE1, STEP_X_LOCAL}; break;        // offt-compute.c:3896-3950
+    case SCHED_SLAB_PX1: steps = {STEP_Z_LOCAL, STEP_PHASE2}; break;        // offt-compute.c:3951-3998
+    case SCHED_PENCIL: steps = {STEP_PHASE1, STEP_PHASE2}; break;           // offt-compute.c:3999-4037
+  }
+  if (inverse) std::reverse(steps.begin(), steps.end());
+  for (Step s : steps) {
+    if (s == STEP_PHASE1 || s == STEP_PHASE2) {
+      if (run_phase(engs, bufs, s == STEP_PHASE1 ? 1 : 2, inverse)) return -1;
+      continue;
+    }
+    for (size_t k = 0; k < engs.size(); ++k) {
+      Engine &E = *engs[k];
+      const Dims d = dims_of(E.po);
+      int rc = 0;
+      if (s == STEP_Z_LOCAL) rc = run_launch(E, sc, ST_K1, L_fftz_local(d, bufs[k].U, bufs[k].A, 0, d.m1), inverse);
+      else if (s == STEP_Y_LOCAL) rc = run_launch(E, sc, ST_K2, L_ffty_local(d, bufs[k].A), inverse);
+      else rc = run_launch(E, sc, ST_K4, L_fftx_local(d, bufs[k].A, bufs[k].U), inverse);
+      if (rc) return -1;
+    }
+  }
+  return 0;
+}
+
+void free_ring(Ring &R) {
+  for (cudaEvent_t e : R.packed) cudaEventDestroy(e);
+  for (cudaEvent_t e : R.recvd) cudaEventDestroy(e);
+  R = Ring();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- create / destroy
+
+int engine_create(struct _offt_plan *po) {
+  World &w = world();
+  if (!w.up) { set_error("no world: call offtb_world_init / offtb_world_init_local (or the compat MPI_Init) first"); return -1; }
+  const int *v = po->params->v;
+  if (check_supported(po->Nx, po->Ny, po->Nz, po->p, v[_P1_])) return -1;
+  if (po->is_r2c) { set_error("real-to-complex plans are not implemented (complex-to-complex only)"); return -1; }
+  if (v[_T1_] < 1 || v[_T2_] < 1 || v[_W1_] < 0 || v[_W2_] < 0 || v[_W1_] > 64 || v[_W2_] > 64) {
+    set_error("tile sizes must be >= 1 and windows in 0..64 (T1 %d W1 %d T2 %d W2 %d)", v[_T1_], v[_W1_], v[_T2_], v[_W2_]);
+    return -1;
+  }
+  Engine *E = new Engine();
+  po->b200 = E;
+  E->po = po;
+  extern int g_default_precision;
+  E->prec = g_default_precision;
+  E->esz = E->prec == PREC_F64 ? 16 : 8;
+  const struct _offt_comm *c = po->comm;
+  E->rank_x = po->rank / c->p2; E->rank_y = po->rank % c->p2;
+  if (po->p == 1) E->sched = SCHED_SINGLE;
+  else if (po->is_oned && c->p1 == 1) E->sched = SCHED_SLAB_1XP;
+  else if (po->is_oned && c->p1 == po->p) E->sched = SCHED_SLAB_PX1;
+  else E->sched = SCHED_PENCIL;
+  E->alloc = alloc_elems(po->Nx, po->Ny, po->Nz, po->p, c->p1);
+  const int Ns[3] = {po->Nx, po->Ny, po->Nz};
+  for (int a = 0; a < 3; ++a)
+    if (make_twiddles(Ns[a], E->prec, &E->tw[a])) return -1;
+  OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comp, cudaStreamNonBlocking));
+  OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comm, cudaStreamNonBlocking));
+  OFFTB_CUDA(cudaEventCreate(&E->ev_begin));
+  OFFTB_CUDA(cudaEventCreate(&E->ev_end));
+  if (!v[_S_]) OFFTB_CUDA(cudaMalloc(&E->d_scratch, (size_t)E->alloc * E->esz));
+  // rings: (W+1) {send, recv} pairs per phase carved from one chunk (set_buffer_chunk / set_buffer,
+  // offt-compute.c:684-746: slot sizes T1*M2*M3*p2 and M1*M4*p1*T2)
+  const Dims d = dims_of(po);
+  const bool use1 = E->sched == SCHED_PENCIL || E->sched == SCHED_SLAB_1XP;
+  const bool use2 = E->sched == SCHED_PENCIL || E->sched == SCHED_SLAB_PX1;
+  long long slot[2] = {use1 ? (long long)d.T1 * d.M2 * d.M3 * d.p2 : 0, use2 ? d.M1 * d.M4 * d.p1 * (long long)d.T2 : 0};
+  int depth[2] = {d.W1 + 1, d.W2 + 1};
+  // The reference lets the two phases share one chunk (set_buffer_chunk, offt-compute.c:684-710).  Here the phases
+  // get disjoint parts: in the fused exchange a rank that has entered phase 2 stores into its peers' phase-2 slots
+  // while a slower peer may still be reading its phase-1 slots, and only same-phase slots are guarded by flags.
+  const long long part[2] = {2 * slot[0] * depth[0], 2 * slot[1] * depth[1]};
+  const long long base[2] = {0, part[0]};
+  const long long need = part[0] + part[1];
+  if (need > 0) OFFTB_CUDA(cudaMalloc(&E->d_ring, (size_t)need * E->esz));
+  for (int ph = 0; ph < 2; ++ph) {
+    Ring &R = E->ring[ph];
+    R.depth = depth[ph]; R.slot_elems = slot[ph];
+    for (int s = 0; s < R.depth; ++s) {
+      R.send.push_back(slot[ph] ? at(E->d_ring, base[ph] + (2LL * s) * slot[ph], E->esz) : nullptr);
+      R.recv.push_back(slot[ph] ? at(E->d_ring, base[ph] + (2LL * s + 1) * slot[ph], E->esz) : nullptr);
+      R.send_off.push_back(base[ph] + (2LL * s) * slot[ph]);
+      R.recv_off.push_back(base[ph] + (2LL * s + 1) * slot[ph]);
+      cudaEvent_t a, b;
+      OFFTB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      OFFTB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      R.packed.push_back(a); R.recvd.push_back(b);
+    }
+  }
+  // exchange mode: kernels that store into the peers' slots (default), or grouped ncclSend/ncclRecv between
+  // send and receive slots (OFFTB_EXCHANGE=nccl, and whenever peer mapping is not possible)
+  const char *xe = getenv("OFFTB_EXCHANGE");
+  const bool want_fused = !(xe && strcmp(xe, "nccl") == 0) && std::max(c->p1, c->p2) <= OFFTB_MAX_GROUP;
+  if (need > 0 && po->p > 1 && want_fused) {
+    if (w.local) {
+      E->xmode = XCHG_FUSED;
+    } else {
+      OFFTB_CUDA(cudaMalloc((void **)&E->d_flags, sizeof(XFlags)));
+      OFFTB_CUDA(cudaMemset(E->d_flags, 0, sizeof(XFlags)));
+      if (world_ipc_share(E->d_ring, E->peer_ring) == 0 && world_ipc_share(E->d_flags, E->peer_flags) == 0) {
+        E->xmode = XCHG_FUSED;
+      } else {
+        if (!po->rank) fprintf(stderr, "offt_b200: peer mapping unavailable (%s); exchanging with NCCL send/recv\n", last_error());
+        world_ipc_release(E->peer_ring);
+        world_ipc_release(E->peer_flags);
+      }
+    }
+  }
+  po->buffer_chunk = E->d_ring;
+  po->buffers1 = &E->ring[0];
+  po->buffers2 = &E->ring[1];
+  return 0;
+}
+
+void engine_destroy(struct _offt_plan *po) {
+  Engine *E = (Engine *)po->b200;
+  if (!E) return;
+  cudaDeviceSynchronize();
+  if (!E->peer_ring.empty() || !E->peer_flags.empty()) {
+    // peers may still be storing flags into this rank's memory: leave together (offt_3d_fin is collective)
+    offtb_world_barrier();
+    world_ipc_release(E->peer_ring);
+    world_ipc_release(E->peer_flags);
+  }
+  cudaFree(E->d_flags);
+  if (E->registered_host) cudaHostUnregister(E->registered_host);
+  for (int a = 0; a < 3; ++a) cudaFree(E->tw[a]);
+  cudaFree(E->d_user); cudaFree(E->d_scratch); cudaFree(E->d_ring);
+  free_ring(E->ring[0]); free_ring(E->ring[1]);
+  for (cudaEvent_t e : E->event_pool) cudaEventDestroy(e);
+  if (E->ev_begin) cudaEventDestroy(E->ev_begin);
+  if (E->ev_end) cudaEventDestroy(E->ev_end);
+  if (E->s_comp) cudaStreamDestroy(E->s_comp);
+  if (E->s_comm) cudaStreamDestroy(E->s_comm);
+  delete E;
+  po->b200 = nullptr;
+  po->buffer_chunk = po->buffers1 = po->buffers2 = nullptr;
+}
+
+// ---------------------------------------------------------------------------------- execute
+
+int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *> &arrays, bool inverse) {
+  std::vector<Engine *> engs;
+  for (auto *po : group) {
+    if (!po || !po->b200) { set_error("plan has no engine"); return -1; }
+    engs.push_back((Engine *)po->b200);
+  }
+  Engine &E0 = *engs[0];
+  cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp;
+  std::vector<Bufs> bufs(engs.size());
+  std::vector<bool> on_host(engs.size(), false);
+  for (size_t k = 0; k < engs.size(); ++k) {
+    Engine &E = *engs[k];
+    E.launches = 0; E.timed.clear(); E.event_next = 0;
+    for (double &m : E.stage_ms) m = 0.0;
+    cudaPointerAttributes attr;
+    cudaError_t pe = cudaPointerGetAttributes(&attr, arrays[k]);
+    if (pe != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+    on_host[k] = !(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    if (on_host[k] && E.async) { set_error("asynchronous execution needs device arrays"); return -1; }
+  }
+  OFFTB_CUDA(cudaEventRecord(E0.ev_begin, sc));
+  for (size_t k = 0; k < engs.size(); ++k) {
+    Engine &E = *engs[k];
+    const size_t bytes = (size_t)E.alloc * E.esz;
+    if (on_host[k]) {
+      if (!E.d_user) OFFTB_CUDA(cudaMalloc(&E.d_user, bytes));
+      if (E.registered_host != arrays[k]) {
+        // pin the caller's array in place once: the reference driver reuses it every repetition
+        if (E.registered_host) { cudaHostUnregister(E.registered_host); E.registered_host = nullptr; }
+        cudaError_t re = cudaHostRegister(arrays[k], bytes, cudaHostRegisterDefault);
+        if (re == cudaSuccess) { E.registered_host = arrays[k]; E.registered_bytes = bytes; }
+        else cudaGetLastError();   // already pinned by the caller, or not pinnable: plain copies still work
+      }
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
+      OFFTB_CUDA(cudaMemcpyAsync(E.d_user, arrays[k], bytes, cudaMemcpyHostToDevice, sc));
+      if (E.stage_timing) { cudaEventRecord(e1, sc); E.timed.push_back({ST_H2D, {e0, e1}}); }
+      bufs[k].U = E.d_user;
+    } else {
+      bufs[k].U = arrays[k];
+    }
+    bufs[k].A = E.d_scratch ? E.d_scratch : bufs[k].U;
+  }
+  if (run_schedule(engs, bufs, inverse)) return -1;
+  for (size_t k = 0; k < engs.size(); ++k) {
+    Engine &E = *engs[k];
+    if (!on_host[k]) continue;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
+    OFFTB_CUDA(cudaMemcpyAsync(arrays[k], E.d_user, (size_t)E.alloc * E.esz, cudaMemcpyDeviceToHost, sc));
+    if (E.stage_timing) { cudaEventRecord(e1, sc); E.timed.push_back({ST_D2H, {e0, e1}}); }
+  }
+  OFFTB_CUDA(cudaEventRecord(E0.ev_end, sc));
+  if (E0.async) return 0;
+  OFFTB_CUDA(cudaStreamSynchronize(sc));
+  OFFTB_CUDA(cudaStreamSynchronize(E0.s_comm));
+  float ms = 0.f;
+  OFFTB_CUDA(cudaEventElapsedTime(&ms, E0.ev_begin, E0.ev_end));
+  for (Engine *Ep : engs) {
+    Ep->last_ms = ms;
+    for (auto &t : Ep->timed) {
+      float m = 0.f;
+      if (cudaEventElapsedTime(&m, t.second.first, t.second.second) == cudaSuccess) Ep->stage_ms[t.first] += m;
+    }
+  }
+  return 0;
+}
+
+}  // namespace offtb

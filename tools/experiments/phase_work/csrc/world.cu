@@ -1,0 +1,182 @@
+// Process-global "world": which rank this process is, on which GPU, and the NCCL
+// communicator that carries the exchanges.  Replaces the reference's implicit
+// MPI_COMM_WORLD (offt-compute.c:3315-3316) and its comm1/comm2 sub-communicators
+// (offt-compute.c:78-125): the row and column groups are addressed as explicit peer lists
+// on the one world communicator.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+namespace offtb {
+
+static char g_error[1024] = "";
+int g_exit_on_error = 1;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+const char *last_error() { return g_error; }
+
+void fatal_or_return(const char *where) {
+  fprintf(stderr, "offt_b200: %s: %s\n", where, g_error);
+  if (g_exit_on_error) exit(-1);
+}
+
+World &world() {
+  static World w;
+  return w;
+}
+
+int world_ipc_share(void *mine, std::vector<void *> &mapped) {
+  World &w = world();
+  mapped.assign(w.size, nullptr);
+  if (!w.nccl) { set_error("world_ipc_share needs an NCCL world"); return -1; }
+  const NcclApi *nc = nccl_api();
+  if (!nc) return -1;
+  cudaIpcMemHandle_t h;
+  OFFTB_CUDA(cudaIpcGetMemHandle(&h, mine));
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  unsigned char *d_all = nullptr;
+  OFFTB_CUDA(cudaMalloc(&d_all, hb * (size_t)w.size));
+  OFFTB_CUDA(cudaMemcpy(d_all + hb * (size_t)w.rank, &h, hb, cudaMemcpyHostToDevice));
+  OFFTB_NCCL(nc->AllGather(d_all + hb * (size_t)w.rank, d_all, hb, ncclUint8, w.nccl, 0));
+  OFFTB_CUDA(cudaStreamSynchronize(0));
+  std::vector<cudaIpcMemHandle_t> all(w.size);
+  OFFTB_CUDA(cudaMemcpy(all.data(), d_all, hb * (size_t)w.size, cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  int rc = 0;
+  for (int r = 0; r < w.size; ++r) {
+    if (r == w.rank) { mapped[r] = mine; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+      mapped[r] = nullptr;
+      rc = -1;
+    }
+  }
+  // all ranks must agree whether the mapping worked
+  int *d_ok = nullptr;
+  OFFTB_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+  const int bad = rc ? 1 : 0;
+  OFFTB_CUDA(cudaMemcpy(d_ok, &bad, sizeof(int), cudaMemcpyHostToDevice));
+  OFFTB_NCCL(nc->AllReduce(d_ok, d_ok, 1, ncclInt, ncclSum, w.nccl, 0));
+  OFFTB_CUDA(cudaStreamSynchronize(0));
+  int total = 0;
+  OFFTB_CUDA(cudaMemcpy(&total, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_ok);
+  if (total) {
+    if (!rc) set_error("peer mapping failed on another rank");
+    world_ipc_release(mapped);
+    return -1;
+  }
+  return 0;
+}
+
+void world_ipc_release(std::vector<void *> &mapped) {
+  World &w = world();
+  for (int r = 0; r < (int)mapped.size(); ++r)
+    if (mapped[r] && r != w.rank) cudaIpcCloseMemHandle(mapped[r]);
+  mapped.clear();
+}
+
+}  // namespace offtb
+
+using namespace offtb;
+
+extern "C" {
+
+const char *offtb_last_error(void) { return last_error(); }
+
+int offtb_set_exit_on_error(int on) { g_exit_on_error = on; return 0; }
+
+void offtb_clear_error(void) { g_error[0] = 0; }
+
+int offtb_get_unique_id(void *id128) {
+  static_assert(sizeof(ncclUniqueId) <= OFFTB_UNIQUE_ID_BYTES, "unique id does not fit");
+  ncclUniqueId id;
+  const NcclApi *nc = nccl_api();
+  if (!nc) return -1;
+  OFFTB_NCCL(nc->GetUniqueId(&id));
+  memset(id128, 0, OFFTB_UNIQUE_ID_BYTES);
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int offtb_world_init(int rank, int size, int device, const void *id128) {
+  World &w = world();
+  if (w.up) { set_error("world already initialised"); return -1; }
+  if (size < 1 || rank < 0 || rank >= size) { set_error("bad rank/size %d/%d", rank, size); return -1; }
+  int ndev = 0;
+  OFFTB_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) { set_error("no CUDA device: this library has no CPU path"); return -1; }
+  if (device < 0) device = rank % ndev;
+  OFFTB_CUDA(cudaSetDevice(device));
+  OFFTB_CUDA(cudaFree(0));
+  if (size > 1) {
+    if (!id128) { set_error("a unique id is required for size > 1"); return -1; }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    const NcclApi *nc = nccl_api();
+    if (!nc) return -1;
+    OFFTB_NCCL(nc->CommInitRank(&w.nccl, size, id, rank));
+  }
+  w.up = true; w.local = false; w.size = size; w.rank = rank; w.device = device;
+  return 0;
+}
+
+int offtb_world_init_local(int size, int device) {
+  World &w = world();
+  if (w.up) { set_error("world already initialised"); return -1; }
+  if (size < 1) { set_error("bad size %d", size); return -1; }
+  int ndev = 0;
+  OFFTB_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) { set_error("no CUDA device: this library has no CPU path"); return -1; }
+  if (device < 0) device = 0;
+  OFFTB_CUDA(cudaSetDevice(device));
+  OFFTB_CUDA(cudaFree(0));
+  w.up = true; w.local = true; w.size = size; w.rank = 0; w.device = device;
+  return 0;
+}
+
+int offtb_world_set_rank(int rank) {
+  World &w = world();
+  if (!w.up || !w.local) { set_error("offtb_world_set_rank needs a local world"); return -1; }
+  if (rank < 0 || rank >= w.size) { set_error("bad rank %d", rank); return -1; }
+  w.rank = rank;
+  return 0;
+}
+
+int offtb_world_size(void) { return world().up ? world().size : 0; }
+int offtb_world_rank(void) { return world().up ? world().rank : -1; }
+
+int offtb_world_barrier(void) {
+  World &w = world();
+  if (!w.up) { set_error("world not initialised"); return -1; }
+  OFFTB_CUDA(cudaDeviceSynchronize());
+  if (w.nccl) {
+    static int *flag = nullptr;
+    if (!flag) OFFTB_CUDA(cudaMalloc(&flag, sizeof(int)));
+    OFFTB_NCCL(nccl_api()->AllReduce(flag, flag, 1, ncclInt, ncclSum, w.nccl, 0));
+    OFFTB_CUDA(cudaStreamSynchronize(0));
+  }
+  return 0;
+}
+
+void offtb_release_finished_plans(void);
+
+void offtb_world_fin(void) {
+  World &w = world();
+  offtb_release_finished_plans();
+  if (!w.up) return;
+  if (w.nccl) { nccl_api()->CommDestroy(w.nccl); w.nccl = nullptr; }
+  w = World();
+}
+
+}  // extern "C"
