@@ -63,3 +63,34 @@ def test_run_fft_ranks_over_offtrun():
     got = _printed(res.stdout)
     assert len(got) == 4, res.stdout[-2000:]
     np.testing.assert_allclose(got, _want(N), rtol=1e-9, atol=1e-2)
+
+
+REF_EXE = ROOT / "oracle" / "_ref" / "run-fft"   # the unmodified reference (library included) over the MPI/FFT shims, on host cores
+
+
+def _lines(out, prefixes):
+    return [l.rstrip() for l in out.splitlines() if l.startswith(prefixes)]
+
+
+@pytest.mark.parametrize("p,flags", [(1, []), (1, ["-S", "1", "-T", "8"]), (4, ["-o", "-d", "4"]), (4, ["-d", "2", "-t", "4", "-w", "1"])])
+def test_same_stdout_as_the_reference_driver(p, flags):
+    """same driver source, two libraries: the reference's own (CPU, shims) and this one (GPU).  Everything the driver
+    prints except the timings must agree: echoed flags, default and final parameter lines, the M/m line, the -v values."""
+    import torch
+    if torch.cuda.device_count() < p:
+        pytest.skip(f"needs {p} GPUs")
+    _need_exe()
+    if not REF_EXE.exists():
+        pytest.skip("oracle/_ref/run-fft not built")
+    N = 64
+    args = ["-N", str(N), "-n", str(N), "-L", str(N), "-r", "1", "-m", "1", "-v", "-a", "0", "-c"] + flags   # -c: is_notest
+    import os
+    ref = subprocess.run([str(REF_EXE)] + args, capture_output=True, text=True, timeout=300, env=dict(os.environ, OFFT_SHIM_NP=str(p)))
+    cmd = [str(EXE)] + args if p == 1 else [str(ROOT / "offt_b200" / "bin" / "offtrun"), "-n", str(p), str(EXE)] + args
+    got = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert ref.returncode == 0 and got.returncode == 0, got.stdout[-1500:] + got.stderr[-1500:]
+    same = ("Nx ", "@ INPUT", "P1 ", "M1 ", "@ FINAL", "set p1", "allocate memory", "p1 ")
+    assert _lines(got.stdout, same) == _lines(ref.stdout, same)
+    a, b = _printed(got.stdout), _printed(ref.stdout)
+    assert len(a) == len(b) == 4
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-3)

@@ -215,3 +215,31 @@ def test_unsupported_inputs_fail_loudly():
     with local_world(3):
         with pytest.raises(ob.OfftError):
             ob.Plan(16, 16, 16, custom={P.P1: 3}, rank=0)   # uneven split
+
+
+def test_async_execution_on_the_callers_stream(oracle):
+    """offtb_plan_set_stream / offtb_plan_set_async: the transform is enqueued on the caller's CUDA stream and
+    offt_3d_execute returns at once; work enqueued before and after it on that stream is ordered around it."""
+    torch = _torch()
+    import offt_b200 as ob
+    N = (64, 128, 256)
+    grid = O.grid_values(21, *N)
+    want = np.fft.fftn(grid)
+    with local_world(1):
+        plan = ob.Plan(*N, is_notest=1, custom={P.P1: 1, P.S: 1})
+        st = torch.cuda.Stream()
+        plan.set_stream(st.cuda_stream)
+        plan.set_async(True)
+        host = torch.from_numpy(grid.reshape(-1).copy()).pin_memory()
+        dev = torch.empty_like(host, device="cuda")
+        out = torch.empty_like(host)
+        with torch.cuda.stream(st):
+            dev.copy_(host, non_blocking=True)      # H2D, the transform and D2H all ride the same stream
+            plan.execute(dev)
+            dev.mul_(2.0)
+            out.copy_(dev, non_blocking=True)
+        st.synchronize()
+        assert O.rel_l2(out.numpy().reshape(N) / 2.0, want) < 1e-12
+        plan.set_async(False)
+        plan.set_stream(0)
+        plan.fin()
