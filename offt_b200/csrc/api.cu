@@ -299,7 +299,7 @@ double offtb_fft_rows(void *data, int n, long long stride, long long dist, long 
 // repair it (ADJUST_POINT), test feasibility, skip points already measured, measure one execute,
 // report; finally install the best point.  The candidate source is a built-in coordinate search over
 // the knobs that matter on a GPU (T1, W1, T2, W2) on the reference's value grid instead of the Active
-// Harmony server ("Tunables").
+// Harmony server (DESIGN.md sections 1 and 5).
 int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose);
 
 int ah_tuning(struct _offt_plan *po, double *in, double *out) { return offtb_tune(po, in, out, po->max_loop, !po->rank); }

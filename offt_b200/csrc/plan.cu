@@ -9,9 +9,12 @@
 // Here every bracket is ONE launch of the batched 1-D kernel (fft_kernels.cuh) whose load and
 // store maps do the (un)packing; z stays the contiguous axis of every intermediate array, so
 // no transpose pass exists and the output layout the caller asked for (_S_, is_equalxy,
-// offt-compute.c:282-313) is produced by the store map of the last launch.  Exchanges run on
-// a second stream as grouped ncclSend/ncclRecv between ring slots (depth W+1); cudaEvents
-// replace MPI_Wait (offt-compute.c:3607-3679, 3789-3861).
+// offt-compute.c:282-313) is produced by the store map of the last launch.  The exchange is
+// fused into the launches on either side of it: the packing launch stores each destination's
+// block into that peer's ring slot over NVLink and flags in peer memory replace MPI_Wait
+// (offt-compute.c:3607-3679, 3789-3861; "fused exchange" below).  Grouped ncclSend/ncclRecv
+// between send and receive slots on a second stream, ordered by cudaEvents, remain as the
+// fallback (OFFTB_EXCHANGE=nccl, or when the peers' rings cannot be mapped).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
