@@ -266,7 +266,7 @@ double offtb_fft_launch_raw(const void *in, void *out, int n, int bits, int sign
   a.in = in; a.out = out; a.tw = tw; a.im = mk(im9); a.om = mk(om9);
   a.load_cfast = load_cfast; a.store_cfast = store_cfast; a.conj = sign > 0;
   a.ry_level = ry_level; a.ry_x0 = ry_x0; a.ry_lo = ry_lo; a.ry_hi = ry_hi;
-  if (c_log < 0) c_log = fft_pick_c_log(info, bits, load_cfast || store_cfast, a.im.B0, nbatch, std::max(a.im.n_lo, a.om.n_lo));
+  if (c_log < 0) c_log = fft_pick_c_log(info, bits, load_cfast || store_cfast, a.im.B0, nbatch, a.im.n_lo, a.om.n_lo);
   a.c_log = c_log;
   if ((info.T << c_log) > info.maxt) { set_error("c_log %d: %d threads exceed the kernel's bound %d", c_log, info.T << c_log, info.maxt); return -1.0; }
   cudaStream_t st = (cudaStream_t)stream;

@@ -48,13 +48,18 @@ int fft_twiddle_table(int N, int prec, long double *out) {
 // Strided axes ("c-fast"): 64 contiguous bytes per transform index, inside one run of the lowest batch digit;
 // 128 bytes when consecutive transform indices are a megabyte or more apart, where every row is its own page
 // and the cost is per row touched (512^3 x pass: 4.6 TB/s at 8 columns, 2.3 at 4).
-int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long n_stride_elems) {
+int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long in_stride_elems,
+                   long long out_stride_elems) {
   const long long esz = prec == PREC_F64 ? 16 : 8;
   long long cmax = std::max(1, info.maxt / info.T);
   cmax = std::min<long long>(cmax, std::max<long long>(1, 220 * 1024 / ((long long)info.colsize * esz)));
   long long c = 1;
   if (cfast) {
-    const long long want = (n_stride_elems * esz >= (1 << 20) ? 128 : 64) / esz;
+    // 128 bytes per index when a side strides by a megabyte or more - if that still leaves room for a ring of two
+    // slots (512 points), or if both sides do (1024 points: 3.3 vs 3.0 TB/s); otherwise 64 bytes keeps two CTAs per SM
+    const bool big_in = in_stride_elems * esz >= (1 << 20), big_out = out_stride_elems * esz >= (1 << 20);
+    const bool ring_fits = 2 * (128 / esz) * (long long)info.colsize * esz <= 220 * 1024;
+    const long long want = (((big_in || big_out) && ring_fits) || (big_in && big_out) ? 128 : 64) / esz;
     while (c * 2 <= want && c * 2 <= cmax && B0 % (unsigned)(c * 2) == 0) c *= 2;
   } else {
     const long long want = std::max<long long>(std::max(1, 64 / info.T), 16384 / ((long long)info.N * esz));

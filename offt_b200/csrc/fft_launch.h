@@ -28,7 +28,8 @@ struct FftShape {
 bool fft_kernel_info(int N, int prec, FftKernelInfo *info);
 
 // log2 of the columns one CTA transforms (see fft_launch.cu)
-int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long n_stride_elems);
+int fft_pick_c_log(const FftKernelInfo &info, int prec, bool cfast, unsigned B0, long long nbatch, long long in_stride_elems,
+                   long long out_stride_elems);
 
 // Launches ceil(nbatch / 2^c_log) CTAs.  nbatch must be a multiple of 2^c_log.
 // Returns cudaSuccess or the launch error.

@@ -160,7 +160,7 @@ cudaEvent_t pool_event(Engine &E) {
 }
 
 int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
-  return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, std::max(L.im.n_lo, L.om.n_lo));
+  return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, L.im.n_lo, L.om.n_lo);
 }
 
 int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
@@ -306,6 +306,33 @@ Launch L_fftx_local(const Dims &d, const void *A, void *U) {
   L.im = mk_map(0, 0, 0, d.dX, d.m3, 1, d.Ny, d.dY, 0);
   L.om = mk_map(0, 0, 0, d.os0, d.m3, d.os2, d.Ny, d.os1, 0);
   L.nbatch = d.m3 * d.Ny; L.load_cfast = true; L.store_cfast = (d.os2 == 1);
+  return L;
+}
+
+// Single rank, x-y-z output (_S_ = 1).  In place, the x pass strides by a whole y-z plane on BOTH sides and every
+// 128-byte piece it touches sits in a page of its own (512^3: 4.5 TB/s).  With one side at the row stride the same
+// pass runs at 5.2 TB/s (tools/kbench.py modes xs / sx), so the z pass - whose stores are whole rows and do not care
+// where a row goes - files row (x, y) of its output as row (y, x) of a scratch array, the x pass reads that at the
+// row stride and stores into the caller's x-y-z layout, and the y pass finishes in place at the row stride.
+Launch L_fftz_swap(const Dims &d, const void *U, void *A) {
+  Launch L = L_fftz_local(d, U, A, 0, d.m1);
+  L.om = mk_map(0, 0, 0, 1, d.m2, d.Nx * d.Nz, d.m1, d.Nz, 0);          // A is [y][x][z]
+  return L;
+}
+Launch L_fftx_swap(const Dims &d, const void *A, void *U) {
+  Launch L;
+  L.N = (int)d.Nx; L.axis = 0; L.in = A; L.out = U;
+  L.im = mk_map(0, 0, 0, d.Nz, d.Nz, 1, d.Ny, d.Nx * d.Nz, 0);          // rows along x at the row stride
+  L.om = mk_map(0, 0, 0, d.os0, d.Nz, d.os2, d.Ny, d.os1, 0);
+  L.nbatch = d.Nz * d.Ny; L.load_cfast = L.store_cfast = true;
+  return L;
+}
+// y pass in the caller's x-y-z array
+Launch L_ffty_out(const Dims &d, void *U) {
+  Launch L;
+  L.N = (int)d.Ny; L.axis = 1; L.in = U; L.out = U;
+  L.im = L.om = mk_map(0, 0, 0, d.os1, d.Nz, d.os2, d.Nx, d.os0, 0);
+  L.nbatch = d.Nz * d.Nx; L.load_cfast = L.store_cfast = true;
   return L;
 }
 
@@ -596,10 +623,14 @@ int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inve
   Engine &E0 = *engs[0];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp;
   // the forward schedule as a list of steps; the backward transform walks it in reverse
-  enum Step { STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL, STEP_PHASE1, STEP_PHASE2 };
+  enum Step { STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL, STEP_PHASE1, STEP_PHASE2, STEP_Z_SWAP, STEP_X_SWAP, STEP_Y_OUT };
   std::vector<Step> steps;
+  const bool swapped = E0.sched == SCHED_SINGLE && E0.po->params->v[_S_] == 1 && E0.d_scratch != nullptr;
   switch (E0.sched) {
-    case SCHED_SINGLE: steps = {STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL}; break;
+    case SCHED_SINGLE:
+      if (swapped) steps = {STEP_Z_SWAP, STEP_X_SWAP, STEP_Y_OUT};
+      else steps = {STEP_Z_LOCAL, STEP_Y_LOCAL, STEP_X_LOCAL};
+      break;
     case SCHED_SLAB_1XP: steps = {STEP_PHASE1, STEP_X_LOCAL}; break;        // offt-compute.c:3896-3950
     case SCHED_SLAB_PX1: steps = {STEP_Z_LOCAL, STEP_PHASE2}; break;        // offt-compute.c:3951-3998
     case SCHED_PENCIL: steps = {STEP_PHASE1, STEP_PHASE2}; break;           // offt-compute.c:3999-4037
@@ -614,7 +645,10 @@ int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inve
       Engine &E = *engs[k];
       const Dims d = dims_of(E.po);
       int rc = 0;
-      if (s == STEP_Z_LOCAL) rc = run_launch(E, sc, ST_K1, L_fftz_local(d, bufs[k].U, bufs[k].A, 0, d.m1), inverse);
+      if (s == STEP_Z_SWAP) rc = run_launch(E, sc, ST_K1, L_fftz_swap(d, bufs[k].U, bufs[k].A), inverse);
+      else if (s == STEP_X_SWAP) rc = run_launch(E, sc, ST_K4, L_fftx_swap(d, bufs[k].A, bufs[k].U), inverse);
+      else if (s == STEP_Y_OUT) rc = run_launch(E, sc, ST_K2, L_ffty_out(d, bufs[k].U), inverse);
+      else if (s == STEP_Z_LOCAL) rc = run_launch(E, sc, ST_K1, L_fftz_local(d, bufs[k].U, bufs[k].A, 0, d.m1), inverse);
       else if (s == STEP_Y_LOCAL) rc = run_launch(E, sc, ST_K2, L_ffty_local(d, bufs[k].A), inverse);
       else rc = run_launch(E, sc, ST_K4, L_fftx_local(d, bufs[k].A, bufs[k].U), inverse);
       if (rc) return -1;
@@ -663,7 +697,10 @@ int engine_create(struct _offt_plan *po) {
   OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comm, cudaStreamNonBlocking));
   OFFTB_CUDA(cudaEventCreate(&E->ev_begin));
   OFFTB_CUDA(cudaEventCreate(&E->ev_end));
-  if (!v[_S_]) OFFTB_CUDA(cudaMalloc(&E->d_scratch, (size_t)E->alloc * E->esz));
+  // a second array: for the transposed output layouts, and for the single-rank x-y-z schedule (see L_fftz_swap);
+  // OFFTB_SINGLE_INPLACE=1 keeps the latter in place (three passes in the caller's array, no scratch)
+  const bool single_swap = E->sched == SCHED_SINGLE && v[_S_] == 1 && !(getenv("OFFTB_SINGLE_INPLACE") && atoi(getenv("OFFTB_SINGLE_INPLACE")));
+  if (!v[_S_] || single_swap) OFFTB_CUDA(cudaMalloc(&E->d_scratch, (size_t)E->alloc * E->esz));
   // rings: (W+1) {send, recv} pairs per phase carved from one chunk (set_buffer_chunk / set_buffer,
   // offt-compute.c:684-746: slot sizes T1*M2*M3*p2 and M1*M4*p1*T2)
   const Dims d = dims_of(po);

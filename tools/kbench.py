@@ -41,6 +41,10 @@ def main():
         "y": ([0, 0, 0, n, n, 1, r1, n * n, 0], None, 1, 1, x),
         "x": ([0, 0, 0, rows, n, 1, r1, n, 0], None, 1, 1, x),
         "xt": ([0, 0, 0, rows, n, 1, r1, n, 0], [0, 0, 0, 1, n, rows, r1, n * n, 0], 1, 0, y),
+        # transform along an axis while swapping the two outer axes: loads at the row stride, stores at the plane stride ...
+        "xs": ([0, 0, 0, n, n, 1, r1, n * n, 0], [0, 0, 0, rows, n, 1, r1, n, 0], 1, 1, y),
+        # ... and the other way round
+        "sx": ([0, 0, 0, rows, n, 1, r1, n, 0], [0, 0, 0, n, n, 1, r1, n * n, 0], 1, 1, y),
     }
     pads = [int(v) for v in a.xpad.split(",")] if a.xpad else []
     if pads:
