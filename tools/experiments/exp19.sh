@@ -1,8 +1,8 @@
 #!/bin/bash
-# lean phase launches built as a variant library (tools/experiments/phase_work): parity + A/B against the product library
+# lean phase launches built as a variant library (tools/experiments/phase_launch.patch applied to a copy of csrc): parity + A/B against the product library
 out=gpurun_out; mkdir -p $out
 n=${1:-2}
-export OFFTB_LIB=$PWD/tools/experiments/phase_work/lib/lib_phase.so
+export OFFTB_LIB=${PHASE_LIB:?path of the variant library built from the patched copy}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "plan_matches or fixture or raw_maps" 2>&1 | tail -2
 timeout 200 $TR --master-port 29631 tests/mgpu_worker.py > $out/mgpu_parity_$n.log 2>&1; echo "parity rc=$?"
