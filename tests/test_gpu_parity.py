@@ -243,3 +243,19 @@ def test_async_execution_on_the_callers_stream(oracle):
         plan.set_async(False)
         plan.set_stream(0)
         plan.fin()
+
+
+@pytest.mark.parametrize("N,bits", [((32, 128, 64), 64), ((128, 16, 256), 32), ((8, 8, 8), 64)])
+def test_single_rank_xyz_schedule(oracle, N, bits):
+    """one rank, _S_ = 1: the schedule that swaps the outer axes in its z pass (plan.cu, L_fftz_swap) - anisotropic
+    grids, both precisions, forward against the oracle and numpy, then backward"""
+    _torch()
+    grid = O.grid_values(17, *N)
+    custom = {P.P1: 1, P.S: 1}
+    want = O.gather_output(oracle.execute(grid, 1, oracle.resolve_params(*N, 1, custom), 0, 0))
+    got, launches, back = gpu_forward(grid, 1, custom, bits=bits, inverse_too=True)
+    assert launches == 3
+    cdt = np.complex128 if bits == 64 else np.complex64
+    A = O.gather_output(got, cdt)
+    assert O.rel_l2(A, want) < TOL[bits] and O.rel_l2(A, np.fft.fftn(grid)) < TOL[bits]
+    assert O.rel_l2(gather_input(got, back, cdt) / np.prod(N), grid) < TOL[bits]
