@@ -175,6 +175,30 @@ def run_port_cpu(N, reps):
     return t, 0
 
 
+def cpu_baseline_of(N, reps=3):
+    """the `cpu_baseline` object of the own arm: a bounded sample of the workload on the host cores (first transform untimed)"""
+    p, cores = host_ranks()
+    S = N
+    while S[0] * S[1] * S[2] > 512 ** 3:
+        S = tuple(max(v // 2, 2) for v in S)
+    try:
+        t, p_used = run_reference_cpu(S, reps, p)
+        best = sum(t[1:]) / len(t[1:])
+        if p_used == 0:   # no compiled reference on this box: the C port, one thread
+            S = run_port_cpu.grid
+            return {"value": round(flops(S) / best / 1e9, 3), "unit": "GFLOP/s", "cores": 1, "kind": "port",
+                    "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), oracle/offt_oracle.c on one thread "
+                              "(oracle/_ref/ref_dump, the compiled reference, is absent on this box)",
+                    "ms_per_step": round(best * 1e3, 2), "host_cores_visible": cores}
+        return {"value": round(flops(S) / best / 1e9, 3), "unit": "GFLOP/s", "cores": p_used, "kind": "reference",
+                "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), slab {p_used}x1, "
+                          f"{p_used} shim-MPI ranks of the unmodified reference (oracle/_ref/ref_dump)",
+                "ms_per_step": round(best * 1e3, 2), "host_cores_visible": cores,
+                "note": "reference pipeline over the stand-in MPI/FFT of oracle/shim (real MPI+FFTW cannot be installed here)"}
+    except Exception as e:   # the checker being absent must not hide the GPU numbers
+        return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -390,32 +414,7 @@ def own_arm(args):
                "timing": "host wall clock around offt_3d_execute(host pointer) + synchronize, max over ranks"}
         del host, keep
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        p, cores = host_ranks()
-        S = N
-        while S[0] * S[1] * S[2] > 512 ** 3:
-            S = tuple(v // 2 for v in S)
-        reps = 3
-        try:
-            t, p_used = run_reference_cpu(S, reps, p)
-            best = sum(t[1:]) / len(t[1:])
-            if p_used == 0:
-                S = run_port_cpu.grid
-                cpu_baseline = {"value": round(flops(S) / best / 1e9, 3), "unit": "GFLOP/s", "cores": 1, "kind": "port",
-                                "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), oracle/offt_oracle.c on one thread "
-                                          "(oracle/_ref/ref_dump, the compiled reference, is absent on this box)",
-                                "ms_per_step": round(best * 1e3, 2), "host_cores_visible": cores}
-                raise StopIteration
-            cpu_baseline = {"value": round(flops(S) / best / 1e9, 3), "unit": "GFLOP/s", "cores": p_used, "kind": "reference",
-                            "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), slab {p_used}x1, "
-                                      f"{p_used} shim-MPI ranks of the unmodified reference (oracle/_ref/ref_dump)",
-                            "ms_per_step": round(best * 1e3, 2), "host_cores_visible": cores,
-                            "note": "reference pipeline over the stand-in MPI/FFT of oracle/shim (real MPI+FFTW cannot be installed here)"}
-        except StopIteration:
-            pass
-        except Exception as e:   # the checker being absent must not hide the GPU numbers
-            cpu_baseline = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    cpu_baseline = cpu_baseline_of(N) if rank == 0 and world == 1 and not args.no_cpu else None
 
     plan.fin()
     ob.world_fin()

@@ -50,3 +50,11 @@ def test_own_arm_fails_loudly_without_a_gpu():
     assert res.returncode != 0
     assert "no CUDA device" in (res.stderr + res.stdout)
     assert not res.stdout.strip().startswith("{")
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "ref_dump").exists(), reason="oracle/_ref/ref_dump not built")
+def test_cpu_baseline_object():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    b = bench.cpu_baseline_of((64, 64, 64))
+    assert b["kind"] == "reference" and b["unit"] == "GFLOP/s" and b["value"] > 0 and b["cores"] >= 1 and "sample" in b
