@@ -177,6 +177,10 @@ int grid_value_floor(int is_index, int **v_list, int *v_list_size, int i, int ra
 int grid_value_ceil(int is_index, int **v_list, int *v_list_size, int i, int raw_v);
 void params_range_setup(struct _offt_plan *po, int **v_list, int *v_list_size);
 int ah_tuning(struct _offt_plan *po, double *in, double *out);
+/* reference offt-tuning.c:80, 144 (the index <-> value hook and the feasibility hook of the tuner) */
+void params_convert(int is_backward, int *v, long *ahv, struct _offt_plan *po, int **v_list, int *v_list_size);
+int is_infeasible_point(struct _offt_plan *po, int *v, int *p_i);
+void params_set_default(struct _offt_plan *po); /* reference offt-compute.c:3127 */
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,8 @@
 //   print_params / offt_print_time  offt-compute.c:3239-3294
 //   params_convert (ADJUST_POINT)   offt-tuning.c:90-118
 //   is_infeasible_point  offt-tuning.c:144-226
-// Written table-driven from those rules; parity is checked against the oracle in
-// tests/test_host_logic.py.
+// Written table-driven from those rules; pinned against the unmodified reference functions themselves
+// (oracle/ref_hooks.c -> tests/test_hooks_vs_reference.py) and against the oracle (tests/test_oracle.py).
 #define OFFT_NO_MINMAX
 #include <algorithm>
 #include <cmath>
@@ -227,6 +227,36 @@ int grid_value_ceil(int is_index, int **v_list, int *v_list_size, int i, int raw
   for (int j = 0; j < v_list_size[i]; ++j)
     if (v_list[i][j] >= raw_v) return is_index ? j : v_list[i][j];
   return raw_v;
+}
+
+// offt-tuning.c:80-136: Active Harmony works in index space (one integer per tunable, an index into its value grid);
+// backward = indices -> values followed by the ADJUST_POINT repairs, forward = values -> indices.  A value or index
+// off the grid is fatal in the reference (printf + exit(-1)); so it is here.
+void params_convert(int is_backward, int *v, long *ahv, struct _offt_plan *po, int **v_list, int *v_list_size) {
+  if (is_backward) {
+    for (int i = 0; i < PARAM_COUNT; ++i) {
+      if (ahv[i] < 0 || ahv[i] >= v_list_size[i]) { printf("params_convert: bwd OUT OF RANGE ERROR\n"); exit(-1); }
+      v[i] = v_list[i][ahv[i]];
+    }
+    params_adjust(po->Nx, po->Ny, po->Nz, po->p, po->is_oned, v);
+  } else {
+    for (int i = 0; i < PARAM_COUNT; ++i) {
+      long found = -1;
+      for (int c = 0; c < v_list_size[i] && found < 0; ++c)
+        if (v_list[i][c] == v[i]) found = c;
+      if (found < 0) { printf("params_convert: fwd OUT OF RANGE ERROR\n"); exit(-1); }
+      ahv[i] = found;
+    }
+  }
+}
+
+// offt-tuning.c:144-226: 1 and the offending tunable in *p_i if the relations among the parameters do not hold
+int is_infeasible_point(struct _offt_plan *po, int *v, int *p_i) { return params_infeasible(po->Nx, po->Ny, po->Nz, po->p, v, p_i); }
+
+// offt-compute.c:3127-3225: heuristic defaults into po->params->v (computed for P1 = floor(sqrt(p)) on the grid,
+// before any -d override, as in the reference)
+void params_set_default(struct _offt_plan *po) {
+  params_default(po->Nx, po->Ny, po->Nz, po->p, po->is_W0, po->is_notest, po->params->v);
 }
 
 void print_params(int *v) {

@@ -51,7 +51,7 @@ def test_library_exports_every_declared_symbol():
     for h in ("offt.h", "offt_b200.h"):
         text = (ROOT / "include" / h).read_text()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        for m in re.finditer(r"\b((?:offt|offtb)_\w+|print_params|ah_tuning|params_range_setup|grid_value_floor|grid_value_ceil)\s*\(", text):
+        for m in re.finditer(r"\b((?:offt|offtb)_\w+|print_params|ah_tuning|params_range_setup|params_set_default|params_convert|is_infeasible_point|grid_value_floor|grid_value_ceil)\s*\(", text):
             names.add(m.group(1))
     assert len(names) > 40
     missing = [n for n in sorted(names) if not hasattr(L, n)]
