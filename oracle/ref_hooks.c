@@ -71,5 +71,14 @@ int main(int argc, char **argv) {
              grid_value_ceil(0, v_list, v_list_size, i, probes[k]), grid_value_floor(1, v_list, v_list_size, i, probes[k]),
              grid_value_ceil(1, v_list, v_list_size, i, probes[k]));
   }
+  /* the two printers of the public API (offt.h:243-244), on fixed inputs */
+  {
+    double t[GES];
+    for (i = 0; i < GES; i++) t[i] = 0.001 * (i + 1) + 0.0000049 * i;
+    printf("print_params: ");
+    print_params(po->params->v);
+    printf("offt_print_time: ");
+    offt_print_time(t);
+  }
   return 0;
 }

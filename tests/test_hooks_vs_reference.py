@@ -36,6 +36,48 @@ def _reference(cfg, npoints, seed):
     return ranges, default, points, fc
 
 
+def _reference_printers(cfg):
+    out = subprocess.run([str(HOOKS)] + [str(v) for v in cfg] + ["0", "1"], capture_output=True, text=True, timeout=120, check=True).stdout
+    lines = {l.split(": ", 1)[0]: l.split(": ", 1)[1] for l in out.splitlines() if l.startswith(("print_params: ", "offt_print_time: "))}
+    return lines["print_params"], lines["offt_print_time"]
+
+
+def _capture_c_stdout(fn):
+    """what a C function of the library writes to stdout"""
+    import os
+    import tempfile
+    libc = C.CDLL(None)
+    sys.stdout.flush()
+    with tempfile.TemporaryFile() as tmp:
+        saved = os.dup(1)
+        os.dup2(tmp.fileno(), 1)
+        try:
+            fn()
+            libc.fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tmp.seek(0)
+        return tmp.read().decode()
+
+
+@pytest.mark.skipif(not HOOKS.exists(), reason="oracle/_ref/ref_hooks not built (needs /root/reference)")
+def test_printers_match_the_reference_byte_for_byte():
+    """print_params and offt_print_time (offt.h:243-244): the lines run-fft.c's users read and scripts parse"""
+    from offt_b200.binding import GES, PARAM_COUNT, lib
+    cfg = (1024, 1024, 1024, 8, 1, 0, 1)
+    want_params, want_time = _reference_printers(cfg)
+    import offt_b200 as ob
+    v = (C.c_int * PARAM_COUNT)(*ob.params_default(*cfg[:4], cfg[5], cfg[6]))
+    t = (C.c_double * GES)(*[0.001 * (i + 1) + 0.0000049 * i for i in range(GES)])
+    lib.print_params.argtypes = [C.POINTER(C.c_int)]
+    lib.print_params.restype = None
+    lib.offt_print_time.argtypes = [C.POINTER(C.c_double)]
+    lib.offt_print_time.restype = None
+    assert _capture_c_stdout(lambda: lib.print_params(v)).rstrip("\n") == want_params
+    assert _capture_c_stdout(lambda: lib.offt_print_time(t)).rstrip("\n") == want_time
+
+
 @pytest.mark.skipif(not HOOKS.exists(), reason="oracle/_ref/ref_hooks not built (needs /root/reference)")
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_hooks_match_the_reference_functions(cfg):
