@@ -53,6 +53,8 @@ World &world();
 // gathered with ncclAllGather.  Returns non-zero (error set) if peer mapping is not possible.
 int world_ipc_share(void *mine, std::vector<void *> &mapped);
 void world_ipc_release(std::vector<void *> &mapped);
+// collective: 0 if `ok` is true on every rank of the world
+int world_agree_ok(bool ok);
 
 // ---- tunables (params.cu) ---------------------------------------------------------------
 std::vector<std::vector<int>> params_grid(int Nx, int Ny, int Nz, int p);
@@ -81,11 +83,13 @@ struct Ring {
 // Flag words of the fused exchange, one block per rank in an IPC-shared allocation.  Peers write them over NVLink.
 //   arrived[phase][j]  : group member j has stored its block of tile number arrived into my landing slot
 //   released[phase][j] : group member j has finished reading the tile number it stored from/into its slot
+#define OFFTB_DONE_SLOTS 32
 struct XFlags {
   unsigned arrived[2][OFFTB_MAX_GROUP];
   unsigned released[2][OFFTB_MAX_GROUP];
-  unsigned done_counter[2][2];   // [phase][writer, reader]
-  unsigned pad[28];
+  // [phase][writer, reader][tile number mod OFFTB_DONE_SLOTS]: launches of a dependent-launch chain overlap, so
+  // consecutive tiles count their finished CTAs in different words
+  unsigned done_counter[2][2][OFFTB_DONE_SLOTS];
 };
 
 enum ExchangeMode { XCHG_NCCL, XCHG_FUSED };
@@ -99,11 +103,17 @@ struct Engine {
   long long alloc = 0;           // complex elements of the caller's array
   void *d_user = nullptr;        // device copy when the caller passes host memory
   void *d_scratch = nullptr;     // second array for the transposed output layouts
-  void *d_ring = nullptr;        // one chunk carved into both phases' rings (they alias, as in the reference)
+  void *d_ring = nullptr;        // one chunk carved into both phases' rings (disjoint parts, see engine_create)
   ExchangeMode xmode = XCHG_NCCL;
   int grid_cap[2] = {0, 0};                // CTA budgets of writer and reader launches while they overlap
   FftShape *dry_shape = nullptr;           // run_launch only reports the launch shape
   XFlags *d_flags = nullptr;               // this rank's flag block
+  unsigned *h_error = nullptr;             // pinned host word the kernels write when a flag wait times out ...
+  unsigned *d_error = nullptr;             // ... and its device alias
+  unsigned long long wait_timeout_ns = 0;  // OFFTB_FLAG_TIMEOUT_S (default 300 s; 0: wait for ever)
+  bool failed = false;                     // an exchange timed out: the plan's flags are no longer consistent
+  int pdl_next = 0;                        // dependent-launch bits of the next launch (run_phase sets, produce/consume read)
+  bool chain_timing = false;               // stage timing of a dependent-launch chain: one event pair per chain
   std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
   std::vector<void *> peer_flags;          // every world rank's flag block as mapped here
   void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz

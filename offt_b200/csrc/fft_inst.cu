@@ -18,7 +18,7 @@ namespace offtb {
 // Ring depth and grid of one launch.  The ring wants two tiles in flight behind the one being
 // transformed (depth 3) when shared memory allows; the grid is one wave of resident CTAs, each
 // walking its share of the tiles.  OFFTB_DEPTH / OFFTB_CTAS_PER_SM override both for experiments.
-template <typename T, class CFG>
+template <typename T, class CFG, bool BULK>
 static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
   const int C = 1 << args.c_log;
   const int threads = CFG::T * C;
@@ -35,12 +35,12 @@ static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
     e = getenv("OFFTB_CTAS_PER_SM");
     env_ctas = e ? atoi(e) : 0;
     // these kernels live on shared memory, not on L1: take the largest shared carve-out
-    cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fft_kernel<T, CFG, BULK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, fft_kernel<T, CFG>);
+    cudaFuncGetAttributes(&fa, fft_kernel<T, CFG, BULK>);
     regs = fa.numRegs;
     smem_optin -= (int)fa.sharedSizeBytes;   // the kernel's static shared memory counts against the same limit
-    cudaError_t ea = cudaFuncSetAttribute(fft_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaError_t ea = cudaFuncSetAttribute(fft_kernel<T, CFG, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
     if (ea != cudaSuccess) { sm_count = 0; return ea; }
   }
   const long long ntiles = nbatch >> args.c_log;
@@ -51,14 +51,27 @@ static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
   // deepest ring that still leaves 16 warps resident per SM (the butterflies need them); else no ring
   const long long per_cta = (ntiles + sm_count - 1) / sm_count;   // tiles a CTA will see at least
   int depth = args.depth > 0 ? args.depth : env_depth, occ = 0;
-  if (depth > 0) {
+  if (args.bulk_store) {
+    // staged bulk stores need a slot that drains while the next tile is worked on: three slots (landing, butterflies,
+    // draining) where shared memory allows, two otherwise; a tile that fills the SM alone keeps the direct stores
+    const int fit = (int)std::min<size_t>(3, (size_t)smem_optin / slot);
+    if (fit >= 2 && (env_depth <= 0 || env_depth >= 2)) {
+      depth = env_depth >= 2 ? std::min(env_depth, fit) : fit;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG, BULK>, threads, slot * depth);
+      if (e != cudaSuccess) return e;
+    } else {
+      args.bulk_store = 0;
+    }
+  }
+  if (args.bulk_store) {
+  } else if (depth > 0) {
     depth = std::min<int>(depth, std::min<int>(4, (int)(smem_optin / slot)));
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG, BULK>, threads, slot * depth);
     if (e != cudaSuccess) return e;
   } else {
     for (depth = args.load_cfast ? 3 : 2; depth >= 1; --depth) {   // contiguous rows: 2 slots measured best
       if (slot * depth > (size_t)smem_optin || (depth > 1 && per_cta < depth)) continue;
-      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG>, threads, slot * depth);
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<T, CFG, BULK>, threads, slot * depth);
       if (e != cudaSuccess) return e;
       if (occ * threads >= 512 || depth == 1) break;
     }
@@ -74,14 +87,31 @@ static cudaError_t plan_one(FftArgs &args, long long nbatch, FftShape *shape) {
   return cudaSuccess;
 }
 
-template <typename T, class CFG>
+template <typename T, class CFG, bool BULK>
 static cudaError_t launch_one(const FftArgs &args_in, long long nbatch, cudaStream_t stream, FftShape *shape_only) {
   FftArgs args = args_in;
   FftShape shape;
-  cudaError_t e = plan_one<T, CFG>(args, nbatch, &shape);
+  cudaError_t e = plan_one<T, CFG, BULK>(args, nbatch, &shape);
+  if constexpr (BULK) {
+    // the tile does not leave room for a draining slot: the plain instantiation with direct stores takes over
+    if (e == cudaSuccess && !args.bulk_store) {
+      FftArgs plain = args_in;
+      plain.bulk_store = 0;
+      return launch_one<T, CFG, false>(plain, nbatch, stream, shape_only);
+    }
+  }
   if (shape_only) *shape_only = shape;
   if (e != cudaSuccess || shape_only || shape.grid == 0) return e;
-  fft_kernel<T, CFG><<<shape.grid, shape.threads, shape.smem, stream>>>(args);
+  if (args.pdl & 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(shape.grid); cfg.blockDim = dim3(shape.threads); cfg.dynamicSmemBytes = shape.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fft_kernel<T, CFG, BULK>, args);
+  }
+  fft_kernel<T, CFG, BULK><<<shape.grid, shape.threads, shape.smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -150,8 +180,12 @@ OFFTB_FFT_CONFIGS(X)
 #undef X
 
 cudaError_t OFFTB_CAT(fft_launch_, OFFTB_INST_N)(int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only) {
-  if (prec == PREC_F64) return launch_one<double, CfgD>(args, nbatch, stream, shape_only);
-  return launch_one<float, CfgF>(args, nbatch, stream, shape_only);
+  if (args.bulk_store) {
+    if (prec == PREC_F64) return launch_one<double, CfgD, true>(args, nbatch, stream, shape_only);
+    return launch_one<float, CfgF, true>(args, nbatch, stream, shape_only);
+  }
+  if (prec == PREC_F64) return launch_one<double, CfgD, false>(args, nbatch, stream, shape_only);
+  return launch_one<float, CfgF, false>(args, nbatch, stream, shape_only);
 }
 
 void OFFTB_CAT(fft_info_, OFFTB_INST_N)(int prec, FftKernelInfo *info) {

@@ -87,6 +87,23 @@ struct FftArgs {
   int signal_count;
   unsigned signal_value;
   unsigned *done_counter;   // zeroed device word, returns to zero after the launch
+  // A flag that does not arrive within wait_timeout_ns (0: wait for ever) makes the CTA store a code into *error_word
+  // (host-visible) and leave without touching data or signalling; the host reports it after the stream has drained.
+  unsigned long long wait_timeout_ns;
+  unsigned *error_word;
+  // dependent-launch chain (plan.cu).  Bit 0: once this launch's CTAs are past their flag wait the next launch of
+  // the stream may start filling the SMs this one leaves; bit 1 (host side): this launch itself is allowed to start
+  // before its predecessor has drained
+  int pdl;
+  // Staged bulk stores (writer launches of the fused exchange).  Remote st.global back-pressures the warps that
+  // issue it and everything queued behind them in the SM's load/store path, so a CTA that scatters its tile over
+  // NVLink cannot load or transform its next tile meanwhile (measured: 580-600 GB/s per direction against 717 for
+  // a kernel that does nothing but store).  With bulk_store the last stage files its results in the tile's
+  // shared-memory slot in destination order - block a of the output is one contiguous run there - and a few
+  // threads hand each run to the TMA engine (cp.async.bulk shared -> global); the slot drains on its own while
+  // the CTA works on the next tile in the next slot.  Needs a ring of >= 2 slots; 3 keeps one tile landing, one
+  // in the butterflies and one draining.  Set by the host when the store map allows it (fft_inst.cu, plan_one).
+  int bulk_store;
 };
 
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
@@ -127,6 +144,15 @@ __device__ __forceinline__ cx<float> ldg_cx(const cx<float> *p) {
   float2 d = __ldg(reinterpret_cast<const float2 *>(p));
   return {d.x, d.y};
 }
+// data stores: the pointer comes out of a table, so tell the compiler it is global memory (STG instead of generic ST)
+template <typename T> __device__ __forceinline__ void st_global(cx<T> *p, cx<T> v) {
+#ifdef OFFTB_ASSUME_GLOBAL_ST
+  // STG instead of the generic ST: measured slower on B200 (512^3 y pass 5.57 -> 4.83 TB/s, transposing x pass
+  // 4.43 -> 3.75, profiles/r02_kernel_ab.md), so the generic store stays
+  __builtin_assume(__isGlobal(p));
+#endif
+  *p = v;
+}
 __device__ __forceinline__ void cp_async_cx(cx<double> *smem_dst, const cx<double> *gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -142,6 +168,21 @@ __device__ __forceinline__ void cp_async_wait(int pending) {
     case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
     default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
+}
+__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most one of this thread's bulk groups still reads its shared-memory source
+__device__ __forceinline__ void bulk_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 template <typename T> __device__ __forceinline__ cx<T> cadd(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ cx<T> csub(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
@@ -206,7 +247,7 @@ __device__ __forceinline__ cx<T> *out_ptr(const FftArgs &a, void *const *s_tab, 
   return (cx<T> *)s_tab[k >> a.om.n_lg] + (bofs + (long long)(k & ((1 << a.om.n_lg) - 1)) * a.om.n_lo);
 }
 
-template <typename T, class CFG, int S>
+template <typename T, class CFG, bool BULK, int S>
 __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg, const FftArgs &a, cx<T> *sm,
                                           void *const *s_tab, long long bofs, unsigned bblock, int t, int s_mul, int s_base, T cj) {
   constexpr int N = CFG::N, E = CFG::E, TT = CFG::T, NS = CFG::NS;
@@ -245,10 +286,13 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
       }
     }
     __syncthreads();
-    fft_stage<T, CFG, S + 1>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
+    fft_stage<T, CFG, BULK, S + 1>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
   } else {
     // ---- last stage: output index beta + (N/R)*k
-    if (a.load_cfast == a.store_cfast) {
+    if constexpr (BULK) {
+      // file the results in the slot in destination order ([k][column] for strided launches, [column][k] for rows),
+      // then one warp hands every block's run to the TMA engine
+      if constexpr (NS > 1) __syncthreads();   // everyone has read this stage's inputs out of the slot
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const int beta = t + TT * u;
@@ -256,7 +300,37 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
         for (int pos = 0; pos < R; ++pos) {
           cx<T> e = v[u * R + pos];
           e.y *= cj;
-          *out_ptr<T>(a, s_tab, bofs, beta + (N / R) * brev(pos, R)) = e;
+          sm[(beta + (N / R) * brev(pos, R)) * s_mul + s_base] = e;
+        }
+      }
+      fence_proxy_async();   // the generic-proxy writes above are ordered before the async-proxy reads below
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int C = 1 << a.c_log;
+        const int nlo = 1 << a.om.n_lg, nblk = N >> a.om.n_lg;
+        const int issuers = (TT << a.c_log) < 32 ? (TT << a.c_log) : 32;   // short transforms run CTAs of fewer than 32 threads
+        if (a.store_cfast) {
+          const long long b0ofs = map_b(a.om, bblock);
+          for (int blk = threadIdx.x; blk < nblk; blk += issuers)
+            bulk_store_issue((cx<T> *)s_tab[blk] + b0ofs, sm + (size_t)blk * nlo * C, (unsigned)(nlo * C * sizeof(cx<T>)));
+        } else {
+          for (int j = threadIdx.x; j < nblk * C; j += issuers) {
+            const int cc = j / nblk, blk = j - cc * nblk;
+            bulk_store_issue((cx<T> *)s_tab[blk] + map_b(a.om, bblock + cc), sm + (size_t)cc * CFG::colsize() + (size_t)blk * nlo,
+                             (unsigned)(nlo * sizeof(cx<T>)));
+          }
+        }
+        bulk_store_commit();
+      }
+    } else if (a.load_cfast == a.store_cfast) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int beta = t + TT * u;
+#pragma unroll
+        for (int pos = 0; pos < R; ++pos) {
+          cx<T> e = v[u * R + pos];
+          e.y *= cj;
+          st_global(out_ptr<T>(a, s_tab, bofs, beta + (N / R) * brev(pos, R)), e);
         }
       }
     } else {
@@ -280,7 +354,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
         else { k = flat & (N - 1); cc = flat / N; }
         cx<T> val = sm[cc * (N + 1) + k];
         val.y *= cj;
-        *out_ptr<T>(a, s_tab, map_b(a.om, bblock + cc), k) = val;
+        st_global(out_ptr<T>(a, s_tab, map_b(a.om, bblock + cc), k), val);
       }
     }
   }
@@ -297,7 +371,31 @@ __device__ __forceinline__ void load_twiddles(cx<T> *wreg, const cx<T> *__restri
   }
 }
 
-template <typename T, class CFG>
+// Peers release the slots a launch writes (or fill the ones it reads) with system-scope stores to this rank's flag
+// words; every CTA waits for all of them before it touches memory.  A peer that never answers (a rank died,
+// mismatched plans) must neither hang the GPU nor kill the context: after wait_timeout_ns (0: wait for ever, like the
+// reference's MPI_Wait) the failure is recorded where the host finds it and the CTA leaves.  Kept out of line so that
+// the transform's register allocation does not depend on it.  Returns true when the CTA must give up.
+static __device__ __noinline__ bool flag_wait(const unsigned *wait_flags, int wait_count, unsigned wait_value,
+                                              unsigned long long wait_timeout_ns, unsigned *error_word, int tid, int nthreads) {
+  int gave_up = 0;
+  for (int j = tid; j < wait_count; j += nthreads) {
+    const volatile unsigned *f = wait_flags + j;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(*f - wait_value) < 0) {
+      __nanosleep(100);
+      if (wait_timeout_ns && global_timer_ns() - t0 > wait_timeout_ns) {
+        if (error_word) *(volatile unsigned *)error_word = 1u + (unsigned)j;
+        gave_up = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  return __syncthreads_or(gave_up) != 0;
+}
+
+template <typename T, class CFG, bool BULK>
 __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_constant__ FftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *sm_all = reinterpret_cast<cx<T> *>(smem_raw);
@@ -315,21 +413,12 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
   const int depth = a.depth;
 
   __shared__ void *s_tab[OFFTB_MAX_GROUP];
+  const unsigned ntiles = a.ntiles;
   for (int j = tid; j < OFFTB_MAX_GROUP; j += nthreads)
     s_tab[j] = a.out_split ? a.out_tab[j] : (void *)((cx<T> *)a.out + (long long)j * a.om.n_hi);
-  if (a.wait_count > 0) {
-    // peers release the slots this launch writes (or fill the ones it reads) with a system-scope store
-    for (int j = tid; j < a.wait_count; j += nthreads) {
-      const volatile unsigned *f = a.wait_flags + j;
-      const long long t0 = clock64();
-      while ((int)(*f - a.wait_value) < 0) {
-        __nanosleep(100);
-        // a peer that never answers (a rank died, mismatched plans) must not hang the GPU: give up after ~10 s
-        if (clock64() - t0 > 20000000000LL) __trap();
-      }
-    }
-    __threadfence_system();
-  }
+  if (a.wait_count > 0 && flag_wait(a.wait_flags, a.wait_count, a.wait_value, a.wait_timeout_ns, a.error_word, tid, nthreads)) return;   // timed out: leave without touching data or signalling
+  // dependent launch: the next kernel of the stream does not consume this one's output (flags order them), let it in
+  if (a.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
 
   constexpr int NW = CFG::twregs(CFG::NS - 1) > 0 ? CFG::twregs(CFG::NS - 1) : 1;
@@ -338,7 +427,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
 
   // this thread's E points of `tile` -> its private places in ring slot `slot`
   auto prefetch = [&](unsigned tile, int slot) {
-    if (tile < a.ntiles) {
+    if (tile < ntiles) {
       const cx<T> *gin = (const cx<T> *)a.in + map_b(a.im, (tile << a.c_log) + c);
       cx<T> *dst = sm_all + slot * slot_elems + tid;
 #pragma unroll
@@ -350,30 +439,8 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
     cp_async_commit();
   };
 
-  unsigned tile = blockIdx.x;
-  for (int d = 0; d + 1 < depth; ++d) prefetch(tile + d * gridDim.x, d);
-  int slot = 0;
-  for (; tile < a.ntiles; tile += gridDim.x) {
-    cx<T> *sm = sm_all + slot * slot_elems;
-    if (depth == 1) {
-      __syncthreads();           // the previous tile's exchange data has been consumed
-      prefetch(tile, 0);
-      cp_async_wait(0);
-    } else {
-      cp_async_wait(depth - 2);  // this tile has landed (the younger groups may still fly)
-    }
-    cx<T> v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      cx<T> x = sm[e * nthreads + tid];
-      x.y *= cj;
-      v[e] = x;
-    }
-    if (depth > 1 || CFG::NS > 1 || a.load_cfast != a.store_cfast) __syncthreads();   // the slot now serves as exchange buffer
-    if (depth > 1) {
-      const int ahead = slot == 0 ? depth - 1 : slot - 1;   // the slot the previous tile has just released
-      prefetch(tile + (unsigned)(depth - 1) * gridDim.x, ahead);
-    }
+  // One tile: its E points are in v, the slot `sm` is free to serve as exchange (and, for bulk launches, staging) buffer
+  auto transform_tile = [&](cx<T> (&v)[E], cx<T> *sm, unsigned tile) {
     const unsigned bblock = tile << a.c_log;
     const long long bofs = map_b(a.om, bblock + c);
 
@@ -384,7 +451,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
       transform = a.ry_lo <= r && r < a.ry_hi;
     }
     if (transform) {
-      fft_stage<T, CFG, 0>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
+      fft_stage<T, CFG, BULK, 0>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
     } else {
 #pragma unroll
       for (int u = 0; u < NU0; ++u)
@@ -392,10 +459,78 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
         for (int i = 0; i < R0; ++i) {
           cx<T> e = v[u * R0 + i];
           e.y *= cj;   // undo the conjugation of the load
-          *out_ptr<T>(a, s_tab, bofs, t + TT * u + (N / R0) * i) = e;
+          st_global(out_ptr<T>(a, s_tab, bofs, t + TT * u + (N / R0) * i), e);
         }
+      if constexpr (BULK) { if (tid < 32) bulk_store_commit(); }   // an empty group keeps the per-tile group count in step
     }
-    slot = slot + 1 == depth ? 0 : slot + 1;
+  };
+
+  if constexpr (!BULK) {
+    // Plain launches: a slot is free again as soon as its tile's exchanges are over, so the ring keeps depth-1 tiles
+    // in flight behind the current one.
+    unsigned tile = blockIdx.x;
+    for (int d = 0; d + 1 < depth; ++d) prefetch(tile + d * gridDim.x, d);
+    int slot = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+      cx<T> *sm = sm_all + slot * slot_elems;
+      if (depth == 1) {
+        __syncthreads();           // the previous tile's exchange data has been consumed
+        prefetch(tile, 0);
+        cp_async_wait(0);
+      } else {
+        cp_async_wait(depth - 2);  // this tile has landed (the younger groups may still fly)
+      }
+      cx<T> v[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        cx<T> x = sm[e * nthreads + tid];
+        x.y *= cj;
+        v[e] = x;
+      }
+      if (depth > 1 || CFG::NS > 1 || a.load_cfast != a.store_cfast) __syncthreads();   // the slot now serves as exchange buffer
+      if (depth > 1) {
+        const int ahead = slot == 0 ? depth - 1 : slot - 1;   // the slot the previous tile has just released
+        prefetch(tile + (unsigned)(depth - 1) * gridDim.x, ahead);
+      }
+      transform_tile(v, sm, tile);
+      slot = slot + 1 == depth ? 0 : slot + 1;
+    }
+  } else {
+    // Bulk-store launches: the slot of the previous tile is still being drained by the TMA engine, so one slot
+    // fewer is available for prefetching (depth-2 tiles ahead) and a slot is re-filled only after warp 0 has seen
+    // its bulk group finish reading.
+    const int ahead_tiles = depth - 2;
+    unsigned tile = blockIdx.x;
+    for (int d = 0; d < ahead_tiles; ++d) prefetch(tile + d * gridDim.x, d);
+    int slot = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+      cx<T> *sm = sm_all + slot * slot_elems;
+      if (ahead_tiles == 0) {
+        if (tid < 32) bulk_store_wait_read1();   // the tile that used this slot two tiles ago has drained
+        __syncthreads();
+        prefetch(tile, slot);
+        cp_async_wait(0);
+      } else {
+        cp_async_wait(ahead_tiles - 1);
+      }
+      cx<T> v[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        cx<T> x = sm[e * nthreads + tid];
+        x.y *= cj;
+        v[e] = x;
+      }
+      if (ahead_tiles > 0 && tid < 32) bulk_store_wait_read1();
+      __syncthreads();   // the slot now serves as exchange and staging buffer
+      if (ahead_tiles > 0) {
+        int ahead = slot + ahead_tiles;   // the slot of the tile before the previous one
+        if (ahead >= depth) ahead -= depth;
+        prefetch(tile + (unsigned)ahead_tiles * gridDim.x, ahead);
+      }
+      transform_tile(v, sm, tile);
+      slot = slot + 1 == depth ? 0 : slot + 1;
+    }
+    if (tid < 32) bulk_store_wait_all();   // every run has reached its destination
   }
   cp_async_wait(0);
   if (a.signal_count > 0) {

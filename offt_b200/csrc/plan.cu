@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 
 #include "engine.h"
@@ -148,6 +149,7 @@ struct Launch {
   unsigned signal_value = 0;
   unsigned *done_counter = nullptr;
   int grid_cap = 0;
+  int pdl = 0;   // bit 0: let the next launch of the stream start early; bit 1: this launch may itself start early
 };
 
 cudaEvent_t pool_event(Engine &E) {
@@ -161,6 +163,37 @@ cudaEvent_t pool_event(Engine &E) {
 
 int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
   return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, L.im.n_lo, L.om.n_lo);
+}
+
+// Can the launch drain its output with TMA bulk stores (fft_kernels.cuh, FftArgs::bulk_store)?  Only launches that
+// scatter into peers' slots want it, and block a of the tile's output must be ONE run in memory laid out like the
+// kernel's shared-memory slot: [k_lo][column] with the CTA's columns adjacent (strided launches, K3's z-chunked
+// slots), or one run of k_lo per column (contiguous rows, K1).  Runs and their addresses must be 16-byte multiples.
+bool bulk_store_ok(const Engine &E, const FftArgs &a, int N) {
+  static const bool env_on = !(getenv("OFFTB_BULK") && atoi(getenv("OFFTB_BULK")) == 0);
+  if (!env_on || !a.out_split || a.om.n_lg >= 30) return false;
+  const long long C = 1LL << a.c_log, nlo = 1LL << a.om.n_lg;
+  if (nlo > N) return false;
+  long long run;
+  if (a.load_cfast && a.store_cfast) {
+    if (a.om.s0 != 1 || (long long)a.om.B0 != C || a.om.n_lo != C) return false;
+    run = nlo * C;
+  } else if (!a.load_cfast && !a.store_cfast) {
+    if (a.om.n_lo != 1) return false;
+    run = nlo;
+  } else {
+    return false;
+  }
+  const long long per16 = 16 / (long long)E.esz;   // elements per 16 bytes: 1 (complex128) or 2 (complex64)
+  if (run % per16) return false;
+  if (per16 > 1) {
+    const bool rows = !a.store_cfast;
+    if (a.om.off % per16 || a.om.s1 % per16 || a.om.s2 % per16 || (rows && a.om.s0 % per16)) return false;
+    // batch digits whose extent is 1 never contribute their stride
+  }
+  for (int j = 0; j < (N >> a.om.n_lg); ++j)
+    if (!a.out_tab[j] || ((uintptr_t)a.out_tab[j] & 15)) return false;
+  return true;
 }
 
 int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
@@ -185,7 +218,10 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   a.wait_flags = L.wait_flags; a.wait_count = L.wait_count; a.wait_value = L.wait_value;
   a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done_counter;
   a.grid_cap = L.grid_cap;
+  a.wait_timeout_ns = E.wait_timeout_ns; a.error_word = E.d_error;
+  a.pdl = L.pdl;
   a.c_log = pick_c_log(E, info, L);
+  a.bulk_store = bulk_store_ok(E, a, L.N) ? 1 : 0;
   if (a.ry_level >= 0 && a.load_cfast != a.store_cfast) { set_error("internal: Ry rule on a transposing launch"); return -1; }
   if (E.dry_shape) {
     cudaError_t se = fft_shape(L.N, E.prec, a, L.nbatch, E.dry_shape);
@@ -193,10 +229,11 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
     return 0;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
+  const bool timed = E.stage_timing && !E.chain_timing;
+  if (timed) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
   cudaError_t err = fft_launch(L.N, E.prec, a, L.nbatch, st);
   if (err != cudaSuccess) { set_error("kernel launch (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(err)); return -1; }
-  if (E.stage_timing) { cudaEventRecord(e1, st); E.timed.push_back({stage, {e0, e1}}); }
+  if (timed) { cudaEventRecord(e1, st); E.timed.push_back({stage, {e0, e1}}); }
   E.launches++;
   return 0;
 }
@@ -490,7 +527,7 @@ int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, in
       L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][me];
     L.signal_count = (int)members.size();
     L.signal_value = seq;
-    L.done_counter = &E.d_flags->done_counter[phase - 1][0];
+    L.done_counter = &E.d_flags->done_counter[phase - 1][0][seq % OFFTB_DONE_SLOTS];
     L.grid_cap = E.grid_cap[0];
   }
   return 0;
@@ -511,7 +548,7 @@ int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
     L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][me];
   L.signal_count = (int)members.size();
   L.signal_value = seq;
-  L.done_counter = &E.d_flags->done_counter[phase - 1][1];
+  L.done_counter = &E.d_flags->done_counter[phase - 1][1][seq % OFFTB_DONE_SLOTS];
   L.grid_cap = E.grid_cap[1];
   return 0;
 }
@@ -531,6 +568,7 @@ int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   Launch L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(E, d, b.A, buf, (long long)tile * d.T2, myT);
   if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 2; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
   if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
+  L.pdl = E.pdl_next;
   return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
 }
 
@@ -543,6 +581,7 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   Launch L = phase == 2 ? L_k4(E, d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
   if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
   if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
+  L.pdl = E.pdl_next;
   return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
 }
 
@@ -583,10 +622,30 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     OFFTB_CUDA(cudaEventRecord(R0.packed[0], sc));
     OFFTB_CUDA(cudaStreamWaitEvent(s2, R0.packed[0], 0));
   }
+  // Dependent-launch chains: on each of the two streams the launches of consecutive tiles are ordered by flags
+  // alone (tile i+1's writer consumes nothing tile i's writer produced), so from the second launch on they carry
+  // the programmatic-serialization attribute and every launch releases its successor once its CTAs are past their
+  // flag wait: the successor's CTAs fill the SMs as this launch's CTAs leave instead of waiting for the last one
+  // (per-tile ramp and tail).  The first launch of a chain is an ordinary one - it does consume what ran before it
+  // on the stream.  Blocked CTAs stay bounded: a launch is released only after its predecessor's CTAs have all
+  // passed their wait, so at most one grid per stream can be spinning and the grid caps still leave the other
+  // stream its share of the SMs.  OFFTB_PDL=0 turns the chains off.
+  static const bool pdl_env = !(getenv("OFFTB_PDL") && atoi(getenv("OFFTB_PDL")) == 0);
+  const bool pdl = two && pdl_env;
+  int n_first = 0, n_second = 0;
+  cudaEvent_t ce[4] = {nullptr, nullptr, nullptr, nullptr};
+  E0.chain_timing = pdl && E0.stage_timing;
+  if (E0.chain_timing) for (cudaEvent_t &e : ce) e = pool_event(E0);
   auto first = [&](Engine &E, const Bufs &b, int i) {
+    E.pdl_next = pdl ? (1 | (n_first ? 2 : 0)) : 0;
+    if (E.chain_timing && !n_first) cudaEventRecord(ce[0], sc);
+    ++n_first;
     return inverse ? consume(engs, E, b, phase, i, tile_T(i), true, sc) : produce(engs, E, b, phase, i, tile_T(i), false, sc);
   };
   auto second = [&](Engine &E, const Bufs &b, int i) {
+    E.pdl_next = pdl ? (1 | (n_second ? 2 : 0)) : 0;
+    if (E.chain_timing && !n_second) cudaEventRecord(ce[2], s2);
+    ++n_second;
     return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, s2) : consume(engs, E, b, phase, i, tile_T(i), false, s2);
   };
   for (int i = 0; i < blocks; ++i) {
@@ -611,6 +670,17 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     for (size_t k = 0; k < engs.size(); ++k)
       if (second(*engs[k], bufs[k], j)) return -1;
   }
+  if (E0.chain_timing) {
+    // one event pair per chain: the span from the first launch's start to the last launch's end, flag waits included
+    cudaEventRecord(ce[1], sc);
+    cudaEventRecord(ce[3], s2);
+    const int st_first = inverse ? (phase == 1 ? ST_K2 : ST_K4) : (phase == 1 ? ST_K1 : ST_K3);
+    const int st_second = inverse ? (phase == 1 ? ST_K1 : ST_K3) : (phase == 1 ? ST_K2 : ST_K4);
+    E0.timed.push_back({st_first, {ce[0], ce[1]}});
+    E0.timed.push_back({st_second, {ce[2], ce[3]}});
+    E0.chain_timing = false;
+  }
+  for (Engine *Ep : engs) Ep->pdl_next = 0;
   if (two) {
     OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
     OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[0], 0));
@@ -714,7 +784,16 @@ int engine_create(struct _offt_plan *po) {
   const long long part[2] = {2 * slot[0] * depth[0], 2 * slot[1] * depth[1]};
   const long long base[2] = {0, part[0]};
   const long long need = part[0] + part[1];
-  if (need > 0) OFFTB_CUDA(cudaMalloc(&E->d_ring, (size_t)need * E->esz));
+  bool ring_ok = true, ring_mine = true;
+  if (need > 0 && cudaMalloc(&E->d_ring, (size_t)need * E->esz) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("ring of %.1f MiB does not fit in device memory (T1 %d W1 %d T2 %d W2 %d)", (double)need * E->esz / 1048576.0, d.T1, d.W1, d.T2, d.W2);
+    E->d_ring = nullptr;
+    ring_ok = ring_mine = false;
+  }
+  // every rank must take the same path from here on: agree whether all rings exist
+  if (w.nccl && po->p > 1 && world_agree_ok(ring_ok) != 0) ring_ok = false;
+  if (!ring_ok) { if (ring_mine) set_error("ring allocation failed on another rank"); return -1; }
   for (int ph = 0; ph < 2; ++ph) {
     Ring &R = E->ring[ph];
     R.depth = depth[ph]; R.slot_elems = slot[ph];
@@ -737,9 +816,20 @@ int engine_create(struct _offt_plan *po) {
     if (w.local) {
       E->xmode = XCHG_FUSED;
     } else {
-      OFFTB_CUDA(cudaMalloc((void **)&E->d_flags, sizeof(XFlags)));
-      OFFTB_CUDA(cudaMemset(E->d_flags, 0, sizeof(XFlags)));
-      if (world_ipc_share(E->d_ring, E->peer_ring) == 0 && world_ipc_share(E->d_flags, E->peer_flags) == 0) {
+      // a rank whose allocations failed still takes part in the collective share (with nothing to offer), so that
+      // all ranks leave it together and agree on the outcome
+      if (cudaMalloc((void **)&E->d_flags, sizeof(XFlags)) != cudaSuccess) { cudaGetLastError(); E->d_flags = nullptr; }
+      if (E->d_flags) cudaMemset(E->d_flags, 0, sizeof(XFlags));
+      if (cudaHostAlloc((void **)&E->h_error, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
+        *E->h_error = 0;
+        if (cudaHostGetDevicePointer((void **)&E->d_error, E->h_error, 0) != cudaSuccess) { cudaGetLastError(); E->d_error = nullptr; }
+      } else { cudaGetLastError(); E->h_error = nullptr; }
+      const char *ts = getenv("OFFTB_FLAG_TIMEOUT_S");
+      const double tsec = ts ? atof(ts) : 300.0;
+      E->wait_timeout_ns = tsec > 0 ? (unsigned long long)(tsec * 1e9) : 0ULL;
+      const int r1 = world_ipc_share(ring_ok ? E->d_ring : nullptr, E->peer_ring);
+      const int r2 = r1 ? -1 : world_ipc_share(E->d_flags, E->peer_flags);
+      if (r1 == 0 && r2 == 0) {
         E->xmode = XCHG_FUSED;
       } else {
         if (!po->rank) fprintf(stderr, "offt_b200: peer mapping unavailable (%s); exchanging with NCCL send/recv\n", last_error());
@@ -759,12 +849,15 @@ void engine_destroy(struct _offt_plan *po) {
   if (!E) return;
   cudaDeviceSynchronize();
   if (!E->peer_ring.empty() || !E->peer_flags.empty()) {
-    // peers may still be storing flags into this rank's memory: leave together (offt_3d_fin is collective)
+    // peers may still be storing flags into this rank's memory: leave together (offt_3d_fin is collective) ...
     offtb_world_barrier();
     world_ipc_release(E->peer_ring);
     world_ipc_release(E->peer_flags);
+    // ... and free the exported allocations only after every importer has closed its mapping of them
+    offtb_world_barrier();
   }
   cudaFree(E->d_flags);
+  if (E->h_error) cudaFreeHost(E->h_error);
   if (E->registered_host) cudaHostUnregister(E->registered_host);
   for (int a = 0; a < 3; ++a) cudaFree(E->tw[a]);
   cudaFree(E->d_user); cudaFree(E->d_scratch); cudaFree(E->d_ring);
@@ -788,6 +881,7 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
     engs.push_back((Engine *)po->b200);
   }
   Engine &E0 = *engs[0];
+  if (E0.failed) { set_error("this plan's exchange timed out earlier; its flags are no longer consistent - destroy it"); return -1; }
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp;
   std::vector<Bufs> bufs(engs.size());
   std::vector<bool> on_host(engs.size(), false);
@@ -837,6 +931,13 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
   if (E0.async) return 0;
   OFFTB_CUDA(cudaStreamSynchronize(sc));
   OFFTB_CUDA(cudaStreamSynchronize(E0.s_comm));
+  if (E0.h_error && *(volatile unsigned *)E0.h_error) {
+    const unsigned code = *(volatile unsigned *)E0.h_error;
+    E0.failed = true;
+    set_error("exchange timed out after %.0f s waiting for group member %u's flag (a peer rank is missing, far behind, or runs a "
+              "different plan; OFFTB_FLAG_TIMEOUT_S sets the limit, 0 waits for ever)", (double)E0.wait_timeout_ns * 1e-9, code - 1);
+    return -1;
+  }
   float ms = 0.f;
   OFFTB_CUDA(cudaEventElapsedTime(&ms, E0.ev_begin, E0.ev_end));
   for (Engine *Ep : engs) {

@@ -33,45 +33,80 @@ World &world() {
   return w;
 }
 
+// 0 if `ok` holds on every rank.  Collective; a rank-local failure inside it still completes the all-reduce where
+// it can, so the other ranks are not left blocked.
+int world_agree_ok(bool ok) {
+  World &w = world();
+  if (!w.nccl) return ok ? 0 : -1;
+  const NcclApi *nc = nccl_api();
+  static int *d_flag = nullptr;
+  bool local_ok = ok && nc != nullptr;
+  if (!d_flag && cudaMalloc(&d_flag, sizeof(int)) != cudaSuccess) { cudaGetLastError(); d_flag = nullptr; }
+  if (!d_flag || !nc) return -1;   // cannot even take part: nothing sane is left to do collectively
+  const int bad = local_ok ? 0 : 1;
+  int total = 1;
+  if (cudaMemcpy(d_flag, &bad, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) cudaGetLastError();
+  const ncclResult_t r = nc->AllReduce(d_flag, d_flag, 1, ncclInt, ncclSum, w.nccl, 0);
+  if (r == ncclSuccess && cudaStreamSynchronize(0) == cudaSuccess && cudaMemcpy(&total, d_flag, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+    return total == 0 ? 0 : -1;
+  cudaGetLastError();
+  return -1;
+}
+
+// Collective: no early return between its first and last collective call - a rank whose own steps fail (no
+// allocation to offer, cudaIpcGetMemHandle, a failed import) offers a zero handle / records the failure, still runs
+// the all-gather and the agreement, and every rank returns the same status.
 int world_ipc_share(void *mine, std::vector<void *> &mapped) {
   World &w = world();
   mapped.assign(w.size, nullptr);
   if (!w.nccl) { set_error("world_ipc_share needs an NCCL world"); return -1; }
   const NcclApi *nc = nccl_api();
-  if (!nc) return -1;
-  cudaIpcMemHandle_t h;
-  OFFTB_CUDA(cudaIpcGetMemHandle(&h, mine));
+  int rc = nc ? 0 : -1;
   const size_t hb = sizeof(cudaIpcMemHandle_t);
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  unsigned char have = 0;
+  if (!rc && mine) {
+    cudaError_t e = cudaIpcGetMemHandle(&h, mine);
+    if (e == cudaSuccess) have = 1;
+    else { cudaGetLastError(); set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); rc = -1; }
+  } else if (!mine) {
+    set_error("nothing to share (allocation failed on this rank)");
+    rc = -1;
+  }
+  // record = handle + one byte "valid"
+  const size_t rb = hb + 8;
+  std::vector<unsigned char> rec(rb, 0), all(rb * (size_t)w.size, 0);
+  memcpy(rec.data(), &h, hb);
+  rec[hb] = have;
   unsigned char *d_all = nullptr;
-  OFFTB_CUDA(cudaMalloc(&d_all, hb * (size_t)w.size));
-  OFFTB_CUDA(cudaMemcpy(d_all + hb * (size_t)w.rank, &h, hb, cudaMemcpyHostToDevice));
-  OFFTB_NCCL(nc->AllGather(d_all + hb * (size_t)w.rank, d_all, hb, ncclUint8, w.nccl, 0));
-  OFFTB_CUDA(cudaStreamSynchronize(0));
-  std::vector<cudaIpcMemHandle_t> all(w.size);
-  OFFTB_CUDA(cudaMemcpy(all.data(), d_all, hb * (size_t)w.size, cudaMemcpyDeviceToHost));
-  cudaFree(d_all);
-  int rc = 0;
-  for (int r = 0; r < w.size; ++r) {
-    if (r == w.rank) { mapped[r] = mine; continue; }
-    cudaError_t e = cudaIpcOpenMemHandle(&mapped[r], all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
-      mapped[r] = nullptr;
-      rc = -1;
+  bool gathered = false;
+  if (nc && cudaMalloc(&d_all, rb * (size_t)w.size) == cudaSuccess) {
+    cudaMemcpy(d_all + rb * (size_t)w.rank, rec.data(), rb, cudaMemcpyHostToDevice);
+    if (nc->AllGather(d_all + rb * (size_t)w.rank, d_all, rb, ncclUint8, w.nccl, 0) == ncclSuccess &&
+        cudaStreamSynchronize(0) == cudaSuccess &&
+        cudaMemcpy(all.data(), d_all, rb * (size_t)w.size, cudaMemcpyDeviceToHost) == cudaSuccess)
+      gathered = true;
+  }
+  if (!gathered) { cudaGetLastError(); if (!rc) set_error("all-gather of the IPC handles failed"); rc = -1; }
+  if (d_all) cudaFree(d_all);
+  if (gathered) {
+    for (int r = 0; r < w.size; ++r) {
+      if (r == w.rank) { mapped[r] = mine; continue; }
+      if (!all[rb * (size_t)r + hb]) { if (!rc) set_error("rank %d has nothing to share", r); rc = -1; continue; }
+      cudaIpcMemHandle_t hr;
+      memcpy(&hr, &all[rb * (size_t)r], hb);
+      cudaError_t e = cudaIpcOpenMemHandle(&mapped[r], hr, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        mapped[r] = nullptr;
+        rc = -1;
+      }
     }
   }
   // all ranks must agree whether the mapping worked
-  int *d_ok = nullptr;
-  OFFTB_CUDA(cudaMalloc(&d_ok, sizeof(int)));
-  const int bad = rc ? 1 : 0;
-  OFFTB_CUDA(cudaMemcpy(d_ok, &bad, sizeof(int), cudaMemcpyHostToDevice));
-  OFFTB_NCCL(nc->AllReduce(d_ok, d_ok, 1, ncclInt, ncclSum, w.nccl, 0));
-  OFFTB_CUDA(cudaStreamSynchronize(0));
-  int total = 0;
-  OFFTB_CUDA(cudaMemcpy(&total, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(d_ok);
-  if (total) {
+  if (world_agree_ok(rc == 0) != 0) {
     if (!rc) set_error("peer mapping failed on another rank");
     world_ipc_release(mapped);
     return -1;
