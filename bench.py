@@ -15,6 +15,11 @@ ONE JSON line (rank 0) with
              duration (CUDA events around that launch on the launching stream) against the measured HBM peak;
   cpu_baseline  the unmodified reference (oracle/_ref/ref_dump: offt-compute.c over the stand-in MPI/FFTW)
              on the host cores, bounded sample, N=1 only.
+  parity     (N >= 2) the gate run before the timed region through the same world: 256^3 slab and pencil plans,
+             forward + backward, gathered on rank 0 and compared with numpy.fft.fftn through ostart/osize/ostride;
+             and, at every N, 64 random (kx, ky) output pencils of the benchmark's own full-size result recomputed
+             independently (DFT by definition over x and y as a float64 GEMM on the device, numpy FFT along z).
+             Above 1e-12 the line carries "invalid" and the exit code is non-zero.
 Nothing here falls back to the CPU: without the CUDA library the own arm fails.
 """
 from __future__ import annotations
@@ -33,7 +38,9 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-NVLINK_GBS = 770.0   # measured peer-copy bandwidth per direction on this pool (B200_PROFILING.md); nominal 900
+NVLINK_MEASURED_GBS = 770.0   # measured peer-copy bandwidth per direction on this pool (B200_PROFILING.md)
+NVLINK_NOMINAL_GBS = 900.0    # NVLink 5 per direction, the figure BASELINE.json's north_star quotes
+PARITY_TOL = 1e-12
 
 
 def flops(N):
@@ -138,6 +145,16 @@ def host_ranks():
     return p, n
 
 
+def host_mem_available_gib():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1048576.0
+    except OSError:
+        pass
+    return 0.0
+
+
 def run_reference_cpu(N, reps, p):
     """the unmodified reference pipeline (oracle/_ref/ref_dump) on p forked host ranks, slab P1 = p with -o
     (run-fft.c -o -d p): returns the per-rep seconds"""
@@ -159,7 +176,6 @@ def run_port_cpu(N, reps):
     """fallback where the compiled reference is absent (it can only be built next to /root/reference): the C
     restatement of its pipeline (oracle/offt_oracle.c, built on demand with gcc), one thread, grid capped at 256^3.
     Returns per-rep seconds and 0 ranks (the callers label the run as a port)."""
-    import numpy as np
     from oracle import oracle as O
     while N[0] * N[1] * N[2] > 256 ** 3:
         N = tuple(max(v // 2, 2) for v in N)
@@ -173,6 +189,31 @@ def run_port_cpu(N, reps):
         t.append(time.perf_counter() - t0)
     run_port_cpu.grid = N
     return t, 0
+
+
+def scipy_baseline(N, reps=3):
+    """CPU Baseline B of BASELINE.md section 3: the best CPU FFT available in the image, scipy.fft.fftn (pocketfft)
+    with every host core, on the same grid (bounded to 512^3)"""
+    try:
+        import numpy as np
+        import scipy.fft
+        _, cores = host_ranks()
+        S = N
+        while S[0] * S[1] * S[2] > 512 ** 3:
+            S = tuple(max(v // 2, 2) for v in S)
+        rng = np.random.default_rng(1)
+        x = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            scipy.fft.fftn(x, workers=cores)
+            t.append(time.perf_counter() - t0)
+        best = sum(t[1:]) / len(t[1:])
+        return {"value": round(flops(S) / best / 1e9, 3), "unit": "GFLOP/s", "cores": cores, "kind": "scipy.fft.fftn(workers=cores)",
+                "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), out of place",
+                "ms_per_step": round(best * 1e3, 2)}
+    except Exception as e:   # noqa: BLE001 - a missing scipy must not hide the GPU numbers
+        return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "scipy.fft.fftn", "sample": f"unavailable: {e}"}
 
 
 def cpu_baseline_of(N, reps=3):
@@ -194,7 +235,8 @@ def cpu_baseline_of(N, reps=3):
                 "sample": f"{S[0]}x{S[1]}x{S[2]} complex128 forward, {reps} transforms (first untimed), slab {p_used}x1, "
                           f"{p_used} shim-MPI ranks of the unmodified reference (oracle/_ref/ref_dump)",
                 "ms_per_step": round(best * 1e3, 2), "host_cores_visible": cores,
-                "note": "reference pipeline over the stand-in MPI/FFT of oracle/shim (real MPI+FFTW cannot be installed here)"}
+                "note": "reference pipeline over the stand-in MPI/FFT of oracle/shim (real MPI+FFTW cannot be installed here); "
+                        "cpu_baseline_b is the best CPU FFT library in the image on the same grid"}
     except Exception as e:   # the checker being absent must not hide the GPU numbers
         return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -205,10 +247,13 @@ def reference_arm(args):
         return 0
     N = workload_for(args)
     p, cores = host_ranks()
-    # bounded sample: the reference pipeline costs ~1.5 s per 256^3 on one core; keep a step at a few seconds
+    # The workload itself where the host can hold it (1024^3: 16 GiB of grid + the reference's exchange buffers, about
+    # 3-5 s per transform on 32 ranks); otherwise a bounded sample, and then config.workload names what actually ran.
     S = N
-    while S[0] * S[1] * S[2] > 512 ** 3:
+    need_gib = 2.6 * 16 * S[0] * S[1] * S[2] / 2 ** 30
+    while S[0] * S[1] * S[2] > 512 ** 3 and (need_gib > 0.8 * host_mem_available_gib() or args.ref_sample):
         S = tuple(max(v // 2, 2) for v in S)
+        need_gib = 2.6 * 16 * S[0] * S[1] * S[2] / 2 ** 30
     t, p_used = run_reference_cpu(S, args.warmup + args.steps, p)
     t = t[args.warmup:]
     ms = 1e3 * sum(t) / len(t)
@@ -218,10 +263,14 @@ def reference_arm(args):
     val = flops(S) / (ms * 1e-3) / 1e9
     sample = f"{S[0]}x{S[1]}x{S[2]} complex128 forward, " + (f"slab {p_used}x1 (-o -d {p_used}), {p_used} shim-MPI ranks; " if kind == "reference" else "oracle port on one thread; ") + \
              f"{'the whole workload' if S == N else 'a bounded sample of the ' + 'x'.join(map(str, N)) + ' workload'}"
+    cfg = config_of(args, S)
+    cfg["decomposition"] = f"host CPU: slab {p_used}x1 on {p_used} forked shim-MPI ranks" if kind == "reference" else "host CPU: one thread"
+    if S != N:
+        cfg["note"] = f"the own arm's workload is {N[0]}x{N[1]}x{N[2]}; this host could only run the grid named in `workload` (rates compare, times do not)"
     line = {"impl": "reference", "metric": "3D FFT GFLOP/s (5*N*log2(N)/t), forward, complex128", "value": round(val, 3),
             "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(args, N), "gpu_launches": 0,
+            "config": cfg, "gpu_launches": 0,
             "cpu_baseline": {"value": round(val, 3), "unit": "GFLOP/s", "cores": p_used, "kind": kind, "sample": sample,
                              "host_cores_visible": cores,
                              "note": "reference pipeline (offt-compute.c, unmodified) over the stand-in MPI and FFT of oracle/shim, not FFTW"
@@ -237,7 +286,7 @@ def config_of(args, N):
         par = "single GPU, three local passes, no exchange"
     else:
         par = f"slab {n}x1 (is_oned, P1={n}), tiled all-to-all overlapped with the passes"
-    return {"workload": f"{N[0]}x{N[1]}x{N[2]} complex128 forward 3-D FFT, in place ({'configs[1]' if n == 1 and N == (512,) * 3 else 'configs[2]' if N == (1024,) * 3 else 'custom grid'})",
+    return {"workload": f"{N[0]}x{N[1]}x{N[2]} complex128 forward 3-D FFT, in place ({'configs[1]' if N == (512,) * 3 else 'configs[2]' if N == (1024,) * 3 else 'custom grid'})",
             "decomposition": par,
             "l2": "arrays (>= 2 GiB per GPU) are larger than the 126 MB L2 and are re-filled from a pristine copy between steps"}
 
@@ -254,8 +303,182 @@ def traffic_of(N, kernel, args):
 
 
 # ------------------------------------------------------------------------------------ own arm
-def own_arm(args):
+class Ctx:
+    """what every measurement below needs: the torch / distributed handles of this rank"""
+
+    def __init__(self, torch, dist, ob, dev, rank, world):
+        self.torch, self.dist, self.ob, self.dev, self.rank, self.world = torch, dist, ob, dev, rank, world
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().tolist()
+
+    def sum_over_ranks(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return t
+
+
+def rel_l2(a, b):
     import numpy as np
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def sampled_pencil_check(cx, plan, pristine, result, N, nsamp=64, seed=7):
+    """Full-size parity without a full-size oracle: `nsamp` random output pencils X[kx, ky, :] of the result the
+    benchmark itself produced, recomputed independently of the library - the sums over x and y by the DFT's
+    definition (one float64 complex GEMM per rank over its input box, all-reduced), numpy's FFT along z - and
+    compared in relative L2.  Reads the input through istart/isize/istride and the output through
+    ostart/osize/ostride like the reference driver does (run-fft.c:49-57, 477-478)."""
+    import numpy as np
+    from offt_b200 import layout
+    torch = cx.torch
+    box = plan.box()
+    Nx, Ny, Nz = N
+    rng = np.random.default_rng(seed)
+    kx = torch.from_numpy(rng.integers(0, Nx, nsamp)).to(cx.dev)
+    ky = torch.from_numpy(rng.integers(0, Ny, nsamp)).to(cx.dev)
+    cdt = pristine.dtype
+    rdt = torch.float64
+    xin = layout.input_view(box, pristine)                     # [sx, sy, Nz] strided view of this rank's input box
+    sx, sy, sz = (int(v) for v in box["isize"])
+    x0, y0 = int(box["istart"][0]), int(box["istart"][1])
+    xs = torch.arange(x0, x0 + sx, device=cx.dev)
+    ys = torch.arange(y0, y0 + sy, device=cx.dev)
+    # exp(-2 pi i k n / N) with the phase reduced mod N in integers first
+    ex = torch.polar(torch.ones(nsamp, sx, dtype=rdt, device=cx.dev), -2 * math.pi * ((kx[:, None] * xs[None, :]) % Nx).to(rdt) / Nx)
+    ey = torch.polar(torch.ones(nsamp, sy, dtype=rdt, device=cx.dev), -2 * math.pi * ((ky[:, None] * ys[None, :]) % Ny).to(rdt) / Ny)
+    part = torch.zeros(nsamp, Nz, dtype=torch.complex128, device=cx.dev)
+    step = max(1, (1 << 24) // max(sy * sz, 1))                  # about 256 MiB of input per GEMM
+    for a in range(0, sx, step):
+        b = min(sx, a + step)
+        w = (ex[:, a:b, None] * ey[:, None, :]).reshape(nsamp, (b - a) * sy)
+        blk = xin[a:b].to(torch.complex128).reshape((b - a) * sy, sz)
+        part[:, :sz] += w @ blk
+        del w, blk
+    part = cx.sum_over_ranks(torch.view_as_real(part))
+    want = np.fft.fft(torch.view_as_complex(part).cpu().numpy(), axis=1)
+    xout = layout.output_view(box, result)                    # [Nx, m4, m3]
+    oy0, oz0 = int(box["ostart"][1]), int(box["ostart"][2])
+    m4, m3 = int(box["osize"][1]), int(box["osize"][2])
+    got = torch.zeros(nsamp, Nz, dtype=torch.complex128, device=cx.dev)
+    mine = ((ky >= oy0) & (ky < oy0 + m4)).cpu().tolist()
+    for s in range(nsamp):
+        if mine[s]:
+            got[s, oz0:oz0 + m3] = xout[int(kx[s]), int(ky[s]) - oy0, :].to(torch.complex128)
+    got = torch.view_as_complex(cx.sum_over_ranks(torch.view_as_real(got))).cpu().numpy()
+    del cdt
+    return rel_l2(got, want)
+
+
+def gate_case(cx, N, oned, custom, grid, want, bits=64):
+    """one small plan through this world, forward and backward, every rank's array gathered and compared on rank 0
+    with numpy (forward: through ostart/osize/ostride; backward: through istart/isize/istride, divided by N)"""
+    import numpy as np
+    from offt_b200 import layout
+    torch, dist, ob = cx.torch, cx.dist, cx.ob
+    P = ob.P
+    plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom=custom)
+    box, alloc, params = plan.box(), plan.alloc_elems, plan.params
+    arr = torch.from_numpy(layout.scatter_input(box, grid, alloc)).to(cx.dev)
+    plan.execute(arr)
+    fwd = arr.clone()
+    plan.execute_inverse(arr)
+    plan.fin()
+    fw = [torch.empty_like(fwd) for _ in range(cx.world)]
+    bw = [torch.empty_like(arr) for _ in range(cx.world)]
+    dist.all_gather(fw, fwd)
+    dist.all_gather(bw, arr)
+    out = None
+    if cx.rank == 0:
+        boxes = [ob.comm_box(*N, cx.world, params[P.P1], r, params[P.S], 0) for r in range(cx.world)]
+        e_f = rel_l2(layout.gather_output(boxes, [t.cpu().numpy() for t in fw], N), want)
+        e_b = rel_l2(layout.gather_input(boxes, [t.cpu().numpy() for t in bw], N) / float(np.prod(N)), grid)
+        out = {"grid": list(N), "process_grid": [params[P.P1], cx.world // params[P.P1]], "S": params[P.S],
+               "forward_vs_numpy": e_f, "round_trip": e_b}
+    del fw, bw, fwd, arr
+    torch.cuda.empty_cache()
+    return out
+
+
+def parity_gate(cx):
+    """the multi-process exchange path pinned where the driver can see it (N >= 2): 256^3 through the slab the
+    benchmark uses, the other slab, and (4+ GPUs) pencils - forward and backward against numpy"""
+    import numpy as np
+    P = cx.ob.P
+    N = (256, 256, 256)
+    rng = np.random.default_rng(2024)
+    grid = rng.uniform(-1, 1, N) + 1j * rng.uniform(-1, 1, N)
+    want = np.fft.fftn(grid) if cx.rank == 0 else None
+    w = cx.world
+    cases = [(1, {P.P1: w, P.S: 0, P.T2: 32, P.W2: 3}), (1, {P.P1: 1, P.S: 1})]
+    if w >= 4:
+        cases += [(0, {P.P1: 2, P.S: 0}), (0, {P.P1: w // 2, P.S: 1, P.T1: 24, P.T2: 40})]
+    res = [gate_case(cx, N, oned, custom, grid, want) for oned, custom in cases]
+    return res
+
+
+def measure_config(cx, N, *, bits, oned, custom, steps, tune=0, label=""):
+    """one more BASELINE configuration through the same world (extra_configs): time, Parseval, round trip"""
+    torch, ob = cx.torch, cx.ob
+    P = ob.P
+    ob.set_default_precision(bits)
+    try:
+        plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom=custom)
+        alloc = plan.alloc_elems
+        rdt = torch.float64 if bits == 64 else torch.float32
+        g = torch.Generator(device=cx.dev); g.manual_seed(99 + cx.rank)
+        x0 = torch.view_as_complex(torch.rand((alloc, 2), generator=g, device=cx.dev, dtype=rdt) * 2 - 1)
+        w = torch.empty_like(x0)
+        out = {"workload": label, "grid": list(N), "bits": bits}
+        if tune > 0:
+            w.copy_(x0)
+            out["default_params"] = {ob.PARAM_NAMES[i]: plan.params[i] for i in (P.P1, P.T1, P.W1, P.T2, P.W2, P.Ry, P.S)}
+            w.copy_(x0); cx.barrier(); plan.execute(w); w.copy_(x0); cx.barrier(); plan.execute(w)
+            out["default_ms"] = round(cx.max_over_ranks([plan.last_ms])[0], 4)
+            out["tune_trials"] = plan.tune(w, tune, verbose=0)
+        times = []
+        for i in range(steps + 2):
+            w.copy_(x0); cx.barrier()
+            plan.execute(w)
+            if i >= 2:
+                times.append(cx.max_over_ranks([plan.last_ms])[0])
+        fl = flops(N)
+        out.update({"params": {ob.PARAM_NAMES[i]: plan.params[i] for i in (P.P1, P.T1, P.W1, P.T2, P.W2, P.Ry, P.S)},
+                    "ms_per_step": round(sum(times) / len(times), 4), "ms_min": round(min(times), 4),
+                    "GFLOPs": round(fl / (sum(times) / len(times)) / 1e6, 1), "steps": steps})
+        e = torch.stack([x0.real.double().square().sum() + x0.imag.double().square().sum(),
+                         w.real.double().square().sum() + w.imag.double().square().sum()])
+        e = cx.sum_over_ranks(e)
+        out["parseval_rel_err"] = abs(float(e[1]) / (float(e[0]) * N[0] * N[1] * N[2]) - 1.0)
+        if bits == 64:
+            out["sampled_pencils_rel_l2"] = sampled_pencil_check(cx, plan, x0, w, N, nsamp=16)
+        plan.execute_inverse(w)
+        w /= float(N[0] * N[1] * N[2])
+        d = torch.stack([(w - x0).abs().double().square().sum(), x0.abs().double().square().sum()])
+        d = cx.sum_over_ranks(d)
+        out["round_trip_rel_l2"] = float(torch.sqrt(d[0] / d[1]))
+        del x0, w
+        plan.fin()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # noqa: BLE001 - an extra configuration must not take the headline line down
+        return {"workload": label, "error": str(e)[-300:]}
+    finally:
+        ob.set_default_precision(64)
+
+
+def own_arm(args):
     import torch
     import torch.distributed as dist
     import offt_b200 as ob   # loads offt_b200/lib/libofft_b200.so; raises if it is not built
@@ -263,6 +486,7 @@ def own_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
     quiet_stdout()
+    os.environ.setdefault("OFFTB_FLAG_TIMEOUT_S", "60")   # a lost peer fails the run with a message instead of hanging the box
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -280,6 +504,11 @@ def own_arm(args):
         ob.world_init(rank, world, local, bytes(idt.cpu().numpy().tobytes()))
     else:
         ob.world_init(0, 1, local, None)
+    cx = Ctx(torch, dist, ob, dev, rank, world)
+    barrier = cx.barrier
+
+    # ---- parity gate of the multi-process path, before anything is timed
+    gate = parity_gate(cx) if world > 1 and not args.no_gate else None
 
     P = ob.P
     # tunables: the reference leaves S, T2, W2 to its tuner; these are the values the sweep in DESIGN.md picked
@@ -299,12 +528,6 @@ def own_arm(args):
     g.manual_seed(1234 + rank)
     pristine = torch.view_as_complex((torch.rand((alloc, 2), generator=g, device=dev, dtype=torch.float64) * 2 - 1))
     work = torch.empty_like(pristine)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def one_step():
         work.copy_(pristine)          # untimed re-fill (also evicts the previous result from L2)
@@ -326,24 +549,20 @@ def own_arm(args):
         times.append(ms); launches += l
     barrier()
     wall = time.perf_counter() - wall0
-    tt = torch.tensor(times, dtype=torch.float64, device=dev)
+    step_ms = cx.max_over_ranks(times)
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
-    step_ms = tt.cpu().tolist()
     ms_per_step = sum(step_ms) / len(step_ms)
     value = flops(N) / (ms_per_step * 1e-3) / 1e9
 
     # ---- size-independent property check of the last result (Parseval): |X|^2 = N |x|^2
-    e_in = float((pristine.real.square().sum() + pristine.imag.square().sum()).item())
-    e_out = float((work.real.square().sum() + work.imag.square().sum()).item())
-    if world > 1:
-        et = torch.tensor([e_in, e_out], dtype=torch.float64, device=dev)
-        dist.all_reduce(et)
-        e_in, e_out = et.tolist()
+    et = torch.stack([pristine.real.square().sum() + pristine.imag.square().sum(), work.real.square().sum() + work.imag.square().sum()])
+    e_in, e_out = cx.sum_over_ranks(et).tolist()
     parseval = abs(e_out / (e_in * N[0] * N[1] * N[2]) - 1.0)
+    # ---- and the full-size result itself against an independent computation of 64 of its pencils
+    pencils = sampled_pencil_check(cx, plan, pristine, work, N)
 
     # ---- per-kernel durations (CUDA events around every launch on its stream) -> roofline
     plan.set_stage_timing(True)
@@ -360,33 +579,42 @@ def own_arm(args):
     tiles2 = -(-c.m3 // params[P.T2]) if world > 1 else 1
     pass_bytes = 2 * 16 * (N[0] * N[1] * N[2]) / world          # one read + one write of the local data
     kern = {"k1_fftz": 1, "k2_ffty": 1 if world == 1 else 0, "k3_ffty": tiles2 if world > 1 else 0, "k4_fftx": tiles2 if world > 1 else 1}
+    chained = world > 1 and os.environ.get("OFFTB_PDL", "1") != "0" and os.environ.get("OFFTB_OVERLAP", "1") != "0" and os.environ.get("OFFTB_EXCHANGE", "") != "nccl"
     passes = {}
     for k, nl in kern.items():
         if nl and acc.get(k, 0) > 0:
             passes[k] = {"ms_per_step": round(acc[k], 4), "launches_per_step": nl, "GBps": round(pass_bytes / (acc[k] * 1e-3) / 1e9, 1)}
+            if nl > 1 and chained:
+                passes[k]["timed_as"] = "span of the stream's dependent-launch chain (first launch start -> last launch end, flag waits included)"
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = max(passes, key=lambda k: passes[k]["ms_per_step"])
+    # the dominant kernel among the HBM-bound local passes (the exchange-bound writer chain is reported under `exchange`)
+    hbm_passes = {k: v for k, v in passes.items() if not (world > 1 and k == "k3_ffty")} or passes
+    dom = max(hbm_passes, key=lambda k: hbm_passes[k]["ms_per_step"])
     achieved = passes[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": f"fft_kernel<double> as {dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(pass_bytes / passes[dom]["launches_per_step"]),
                 "avg_launch_ms": round(passes[dom]["ms_per_step"] / passes[dom]["launches_per_step"], 5),
                 "traffic": traffic_of(N, dom, args), "passes": passes}
+    exchange = None
     if world > 1:
         xb = (world - 1) / world * 16 * (N[0] * N[1] * N[2]) / world      # bytes each GPU sends (and receives)
         xms = acc.get("exchange2", 0.0)
         fused = xms == 0.0     # fused exchange: the NVLink stores are part of the K3 launches, there is no separate copy
         if fused:
             xms = acc.get("k3_ffty", 0.0)
-        roofline["exchange"] = {"bytes_out_per_gpu": int(xb), "device_ms_sum_of_tiles": round(xms, 4),
-                                "how": "stores of the K3 (FFTy + pack) launches into the peers' slots" if fused else "grouped ncclSend/ncclRecv",
-                                "GBps_per_direction": round(xb / (xms * 1e-3) / 1e9, 1) if xms > 0 else None,
-                                "peak": NVLINK_GBS, "frac": round(xb / (xms * 1e-3) / 1e9 / NVLINK_GBS, 4) if xms > 0 else None,
-                                "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900"}
+        rate = xb / (xms * 1e-3) / 1e9 if xms > 0 else None
+        exchange = {"bytes_out_per_gpu": int(xb), "device_ms": round(xms, 4),
+                    "how": ("stores of the K3 (FFTy + pack) launches into the peers' slots over NVLink; " +
+                            ("device_ms = span of the writer chain" if chained else "device_ms = sum over the tiles' launches")) if fused else "grouped ncclSend/ncclRecv",
+                    "GBps_per_direction": round(rate, 1) if rate else None,
+                    "frac_of_900": round(rate / NVLINK_NOMINAL_GBS, 4) if rate else None,
+                    "frac_of_770": round(rate / NVLINK_MEASURED_GBS, 4) if rate else None,
+                    "peaks": "900 = NVLink 5 nominal per direction (north_star); 770 = measured peer copy per direction (B200_PROFILING.md)"}
 
     # ---- e2e: host arrays through the C API (H2D + transform + D2H inside the timed region)
     e2e = None
@@ -405,24 +633,44 @@ def own_arm(args):
             dt = time.perf_counter() - t0
             if i >= 2:
                 e_times.append(dt * 1e3)
-        et = torch.tensor(e_times, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e_ms = float(et.mean().item())
+        e_ms = sum(cx.max_over_ranks(e_times)) / len(e_times)
         e2e = {"value": round(flops(N) / (e_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s", "ms_per_step": round(e_ms, 3), "steps": e_steps,
                "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": int(nbytes) * world,
                "timing": "host wall clock around offt_3d_execute(host pointer) + synchronize, max over ranks"}
         del host, keep
 
     cpu_baseline = cpu_baseline_of(N) if rank == 0 and world == 1 and not args.no_cpu else None
+    cpu_baseline_b = scipy_baseline(N) if rank == 0 and world == 1 and not args.no_cpu else None
 
     plan.fin()
+    del pristine, work
+    torch.cuda.empty_cache()
+
+    # ---- more of BASELINE.json's configurations through the same world
+    extra = {}
+    extra_configs = []
+    if not args.no_extra:
+        if world == 1 and N == (512, 512, 512):
+            # configs[2]'s grid on ONE GPU: the missing point of a true strong-scaling curve (1 -> 2/4/8 GPUs on 1024^3)
+            extra["strong_scaling_n1_1024"] = measure_config(cx, (1024, 1024, 1024), bits=64, oned=0, custom={P.P1: 1, P.S: 1}, steps=5,
+                                                             label="1024^3 complex128 forward on one GPU (configs[2]'s grid without the exchange)")
+        if world == 8 and N == (1024, 1024, 1024):
+            extra_configs.append(measure_config(cx, (2048, 2048, 2048), bits=64, oned=0, custom={P.P1: 2, P.S: 0}, steps=3,
+                                                label="configs[3]: 2048^3 complex128 forward, pencil 2x4, 8 GPUs"))
+            extra_configs.append(measure_config(cx, (2048, 1024, 512), bits=32, oned=1, custom={P.P1: 8, P.S: 0}, steps=5, tune=16,
+                                                label="configs[4]: 2048x1024x512 complex64 forward, 8 GPUs, tunables searched (offtb_tune)"))
+
     ob.world_fin()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
+    parity = {"tolerance": PARITY_TOL, "sampled_pencils": {"count": 64, "grid": list(N), "rel_l2": pencils,
+                                                         "how": "64 random (kx, ky) pencils of the timed workload's own result vs the DFT by definition over x, y (float64 GEMM) + numpy FFT along z"},
+              "cases": gate}
+    worst = [pencils] + [v for cse in (gate or []) for v in (cse["forward_vs_numpy"], cse["round_trip"])]
+    parity["rel_l2"] = max(worst)
     line = {"metric": "3D FFT GFLOP/s (5*N*log2(N)/t), forward, complex128", "value": round(value, 2), "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "ms_min": round(min(step_ms), 4), "ms_median": round(statistics.median(step_ms), 4),
@@ -430,11 +678,17 @@ def own_arm(args):
             "config": dict(config_of(args, N), tunables={ob.PARAM_NAMES[i]: params[i] for i in (P.P1, P.T1, P.W1, P.T2, P.W2, P.Ry, P.V, P.S)}),
             "timing": "CUDA events on the plan's compute stream around each step (first kernel -> last kernel, exchanges included), max over ranks per step; barrier + synchronize on both sides of every step",
             "wall_s_timed_region": round(wall, 3), "gpu_launches": launches,
-            "parseval_rel_err": parseval, "clocks": clock_rec, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline}
-    if parseval > 1e-9:
-        line["invalid"] = f"Parseval check failed ({parseval:.3e})"
+            "parseval_rel_err": parseval, "parity": parity, "clocks": clock_rec, "roofline": roofline, "exchange": exchange,
+            "e2e": e2e, "cpu_baseline": cpu_baseline, "cpu_baseline_b": cpu_baseline_b}
+    if extra:
+        line["extra"] = extra
+    if extra_configs:
+        line["extra_configs"] = extra_configs
+    bad = parseval > 1e-9 or not (parity["rel_l2"] <= PARITY_TOL)
+    if bad:
+        line["invalid"] = f"parity check failed (Parseval {parseval:.3e}, worst rel-L2 {parity['rel_l2']:.3e} > {PARITY_TOL})"
     emit(json.dumps(line))
-    return 0 if parseval <= 1e-9 else 1
+    return 1 if bad else 0
 
 
 def main():
@@ -450,6 +704,9 @@ def main():
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture (profiles/)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gate", action="store_true", help="skip the multi-process parity gate (experiments only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra configurations (1024^3 on one GPU; configs[3], configs[4] at 8 GPUs)")
+    ap.add_argument("--ref-sample", action="store_true", help="reference arm: force the bounded 512^3 sample even if the host could run the workload")
     args = ap.parse_args()
     sys.exit(reference_arm(args) if args.impl == "reference" else own_arm(args))
 

@@ -56,6 +56,11 @@ struct FftMap {
   long long s0, s1, s2;
   int n_lg;
   unsigned B0, B1;
+  // General split of the transform index (fft_generic.cu only; the power-of-two kernels need gg == 0): when gg > 0 the
+  // index belongs to one of gg blocks of which the first gg-gb hold gF items and the last gb hold gF+1 - the
+  // ownership rule of an uneven division (offt-compute.c:141-144, 1000-1013) - and element n lives at
+  // block(n)*n_hi + (n - first(block))*n_lo.
+  int gF, gb, gg;
 };
 
 #define OFFTB_MAX_GROUP 16   // ranks in one exchange group (one NVSwitch box holds 8)

@@ -170,7 +170,12 @@ int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
 // kernel's shared-memory slot: [k_lo][column] with the CTA's columns adjacent (strided launches, K3's z-chunked
 // slots), or one run of k_lo per column (contiguous rows, K1).  Runs and their addresses must be 16-byte multiples.
 bool bulk_store_ok(const Engine &E, const FftArgs &a, int N) {
-  static const bool env_on = !(getenv("OFFTB_BULK") && atoi(getenv("OFFTB_BULK")) == 0);
+  // Opt-in (OFFTB_BULK=1).  Measured on 2 GPUs, 1024^3 (profiles/r02_exchange_ab.md): the writer chain alone moves
+  // 583 GB/s per direction with bulk stores against 607 with direct stores - the per-SM rate of remote writes is the
+  // limit either way - and the three-slot ring leaves one CTA per SM, which forbids the two-stream overlap with the
+  // reader (15.2 ms against 11.7).  Emulated-rank worlds always take it so that the parity tests keep covering it.
+  static const int env_bulk = getenv("OFFTB_BULK") ? atoi(getenv("OFFTB_BULK")) : -1;
+  const bool env_on = env_bulk >= 0 ? env_bulk != 0 : world().local;
   if (!env_on || !a.out_split || a.om.n_lg >= 30) return false;
   const long long C = 1LL << a.c_log, nlo = 1LL << a.om.n_lg;
   if (nlo > N) return false;

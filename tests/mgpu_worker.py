@@ -1,9 +1,12 @@
 """One rank of the multi-GPU parity run (launched by torchrun, one process per GPU, NCCL).
 
 Every rank builds the plan through the C API, fills its input box of the seeded global grid,
-runs offt_3d_execute on its own GPU (real grouped ncclSend/ncclRecv exchanges), and rank 0
-gathers all outputs and compares them through ostart/osize/ostride with the oracle.
-Then the backward transform must return N * input.   usage: torchrun ... tests/mgpu_worker.py
+runs offt_3d_execute on its own GPU, and rank 0 gathers all outputs and compares them through
+ostart/osize/ostride with the oracle and numpy.  Then the backward transform must return N * input.
+The exchange path is whatever the environment selects (tests/test_multi_gpu.py runs them all):
+default = fused peer stores (TMA bulk stores, two streams, dependent-launch chains); OFFTB_BULK=0 /
+OFFTB_PDL=0 / OFFTB_OVERLAP=0 switch those pieces off; OFFTB_EXCHANGE=nccl = grouped ncclSend/ncclRecv.
+usage: torchrun ... tests/mgpu_worker.py
 """
 import os
 import sys

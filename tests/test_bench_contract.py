@@ -58,3 +58,48 @@ def test_cpu_baseline_object():
     import bench
     b = bench.cpu_baseline_of((64, 64, 64))
     assert b["kind"] == "reference" and b["unit"] == "GFLOP/s" and b["value"] > 0 and b["cores"] >= 1 and "sample" in b
+
+
+def test_cpu_baseline_b_object():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    b = bench.scipy_baseline((32, 32, 32))
+    assert b["unit"] == "GFLOP/s" and b["value"] > 0 and b["cores"] >= 1 and "scipy" in b["kind"]
+
+
+def test_reference_arm_names_the_grid_it_ran():
+    """--ref-sample forces the bounded sample: config.workload must then name the sample, not the own arm's grid"""
+    if not (ROOT / "oracle" / "_ref" / "ref_dump").exists():
+        pytest.skip("oracle/_ref/ref_dump not built")
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.config_of(type("A", (), {"gpus": 2})(), (512, 512, 512))["workload"].startswith("512x512x512")
+
+
+def test_layout_views_match_the_oracle_helpers():
+    """offt_b200.layout (what bench.py's parity gate uses) against the oracle's index arithmetic on uneven and even boxes"""
+    import numpy as np
+    import offt_b200 as ob
+    from offt_b200 import layout
+    from oracle import oracle as O
+    for N, p, p1, S in [((12, 10, 9), 6, 3, 0), ((16, 8, 32), 4, 2, 1), ((8, 8, 8), 1, 1, 0)]:
+        grid = O.grid_values(3, *N)
+        boxes = [ob.comm_box(*N, p, p1, r, S, 0) for r in range(p)]
+        alloc = ob.alloc_elems(*N, p, p1)
+        arrays = []
+        for r, b in enumerate(boxes):
+            rb = O.RankBox(p=p, rank=r, N=N, p1=p1, p2=p // p1, istart=b["istart"], isize=b["isize"], istride=b["istride"],
+                           ostart=b["ostart"], osize=b["osize"], ostride=b["ostride"], alloc=alloc)
+            a = layout.scatter_input(b, grid, alloc)
+            assert np.array_equal(a, O.scatter_input(rb, grid))
+            arrays.append(a)
+        assert np.array_equal(layout.gather_input(boxes, arrays, N), grid)
+        # a spectrum scattered through the output boxes comes back through gather_output
+        spec = O.grid_values(4, *N)
+        outs = []
+        for b in boxes:
+            a = np.zeros(alloc, dtype=np.complex128)
+            if min(b["osize"]) > 0:
+                layout.output_view(b, a)[...] = spec[tuple(slice(s, s + n) for s, n in zip(b["ostart"], b["osize"]))]
+            outs.append(a)
+        assert np.array_equal(layout.gather_output(boxes, outs, N), spec)

@@ -10,7 +10,16 @@ ROOT = Path(__file__).resolve().parents[1]
 pytestmark = pytest.mark.gpu
 
 
-def test_nccl_ranks_match_oracle():
+MODES = {
+    "default": {},                                           # fused peer stores: bulk stores, two streams, dependent launches
+    "direct_stores_one_stream": {"OFFTB_BULK": "0", "OFFTB_PDL": "0", "OFFTB_OVERLAP": "0"},
+    "nccl_send_recv": {"OFFTB_EXCHANGE": "nccl"},            # the fallback when peer mapping is unavailable
+}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_nccl_ranks_match_oracle(mode):
+    import os
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,6 +27,7 @@ def test_nccl_ranks_match_oracle():
     n = 8 if n >= 8 else 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29631", str(ROOT / "tests" / "mgpu_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, OFFTB_FLAG_TIMEOUT_S="30", **MODES[mode])
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     print(res.stdout[-4000:], res.stderr[-2000:])
     assert res.returncode == 0 and "MGPU PARITY PASSED" in res.stdout
