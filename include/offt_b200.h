@@ -43,6 +43,9 @@ void offtb_clear_error(void);
 /* precision for plans created afterwards: 64 (default, the reference's only mode) or 32 */
 int offtb_set_default_precision(int bits);
 int offtb_plan_precision(const struct _offt_plan *po);
+/* 1: every launch runs on the any-length kernel (fft_generic.cu) also where a power-of-two kernel exists - parity tests
+ * of that kernel at sizes the fast kernels normally take; 0 (default): only where it is needed (other lengths, uneven splits) */
+int offtb_set_force_generic(int on);
 /* run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = the plan's own */
 int offtb_plan_set_stream(struct _offt_plan *po, void *stream);
 /* 1: offt_3d_execute returns right after enqueueing (device pointers only) */

@@ -7,6 +7,6 @@ transform, and importing `offt_b200.binding` fails loudly if the library is not 
 """
 from .binding import (  # noqa: F401
     LIB_PATH, OfftError, Plan, PARAM_NAMES, P, lib, world_init, world_init_local, world_fin, world_size,
-    world_rank, get_unique_id, set_default_precision, execute_group, fft_launch_raw, fft_rows,
+    world_rank, get_unique_id, set_default_precision, set_force_generic, execute_group, fft_launch_raw, fft_rows,
     params_default, params_range, is_infeasible_point, params_adjust, comm_box, alloc_elems, check_supported,
 )

@@ -140,6 +140,10 @@ def world_rank() -> int:
     return lib.offtb_world_rank()
 
 
+def set_force_generic(on: bool):
+    _check(lib.offtb_set_force_generic(int(on)), "offtb_set_force_generic")
+
+
 def set_default_precision(bits: int):
     _check(lib.offtb_set_default_precision(bits), "offtb_set_default_precision")
 

@@ -4,12 +4,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "engine.h"
 
 namespace offtb {
 int g_default_precision = PREC_F64;
+int g_force_generic = getenv("OFFTB_GENERIC") ? atoi(getenv("OFFTB_GENERIC")) : 0;
 
 static double now_s() {
   using namespace std::chrono;
@@ -199,6 +201,7 @@ int offtb_set_default_precision(int bits) {
   g_default_precision = bits;
   return 0;
 }
+int offtb_set_force_generic(int on) { g_force_generic = on ? 1 : 0; return 0; }
 int offtb_plan_precision(const struct _offt_plan *po) { return eng(po) ? eng(po)->prec : -1; }
 int offtb_plan_set_stream(struct _offt_plan *po, void *stream) {
   if (!eng(po)) { set_error("null plan"); return -1; }
@@ -235,7 +238,8 @@ double offtb_fft_launch_raw(const void *in, void *out, int n, int bits, int sign
                             const long long *im9, const long long *om9, int c_log, int load_cfast, int store_cfast,
                             int ry_level, int ry_x0, int ry_lo, int ry_hi, int repeat, void *stream) {
   FftKernelInfo info;
-  if (!fft_kernel_info(n, bits, &info)) { set_error("unsupported length %d", n); return -1.0; }
+  const bool generic = g_force_generic > 0 || !fft_kernel_info(n, bits, &info);
+  if (generic && (n < 1 || (size_t)n > fft_generic_max_n(bits))) { set_error("unsupported length %d", n); return -1.0; }
   auto mk = [](const long long *m) {
     FftMap f;
     f.off = m[0];
@@ -244,16 +248,15 @@ double offtb_fft_launch_raw(const void *in, void *out, int n, int bits, int sign
     f.n_lg = lg; f.n_hi = m[2]; f.n_lo = m[3];
     f.B0 = (unsigned)(m[4] > 0 ? m[4] : 1); f.s0 = m[5];
     f.B1 = (unsigned)(m[6] > 0 ? m[6] : 1); f.s1 = m[7]; f.s2 = m[8];
+    f.gF = f.gb = f.gg = 0;
     return f;
   };
   const size_t esz = bits == 64 ? 16 : 8;
-  static void *tw_cache[16][2] = {{nullptr}};
-  int slot = 0;
-  while ((1 << slot) < n) ++slot;
-  void *&tw = tw_cache[slot][bits == 64 ? 0 : 1];
+  static std::map<long long, void *> tw_cache;   // (length, precision, table kind) -> device table
+  void *&tw = tw_cache[((long long)n << 2) | (bits == 64 ? 0 : 1) | (generic ? 2 : 0)];
   if (!tw) {
     std::vector<long double> tab(2 * (size_t)n + 2);
-    const int count = fft_twiddle_table(n, bits, tab.data());
+    const int count = generic ? fft_generic_twiddle_table(n, tab.data()) : fft_twiddle_table(n, bits, tab.data());
     const size_t cnt = (size_t)std::max(count, 1);
     std::vector<double> hd(2 * cnt);
     std::vector<float> hf(2 * cnt);
@@ -266,15 +269,17 @@ double offtb_fft_launch_raw(const void *in, void *out, int n, int bits, int sign
   a.in = in; a.out = out; a.tw = tw; a.im = mk(im9); a.om = mk(om9);
   a.load_cfast = load_cfast; a.store_cfast = store_cfast; a.conj = sign > 0;
   a.ry_level = ry_level; a.ry_x0 = ry_x0; a.ry_lo = ry_lo; a.ry_hi = ry_hi;
-  if (c_log < 0) c_log = fft_pick_c_log(info, bits, load_cfast || store_cfast, a.im.B0, nbatch, a.im.n_lo, a.om.n_lo);
-  a.c_log = c_log;
-  if ((info.T << c_log) > info.maxt) { set_error("c_log %d: %d threads exceed the kernel's bound %d", c_log, info.T << c_log, info.maxt); return -1.0; }
+  if (!generic) {
+    if (c_log < 0) c_log = fft_pick_c_log(info, bits, load_cfast || store_cfast, a.im.B0, nbatch, a.im.n_lo, a.om.n_lo);
+    a.c_log = c_log;
+    if ((info.T << c_log) > info.maxt) { set_error("c_log %d: %d threads exceed the kernel's bound %d", c_log, info.T << c_log, info.maxt); return -1.0; }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
   for (int r = 0; r < (repeat > 0 ? repeat : 1); ++r) {
-    cudaError_t err = fft_launch(n, bits, a, nbatch, st);
+    cudaError_t err = generic ? fft_generic_launch(n, bits, a, nbatch, st, nullptr) : fft_launch(n, bits, a, nbatch, st);
     if (err != cudaSuccess) { set_error("launch: %s", cudaGetErrorString(err)); return -1.0; }
   }
   cudaEventRecord(e1, st);

@@ -21,6 +21,7 @@ const char *last_error();
 // what the reference does on a fatal condition (printf + exit(-1), offt-compute.c:3440-3443);
 // bindings that want a return code instead call offtb_set_exit_on_error(0)
 extern int g_exit_on_error;
+extern int g_force_generic;   // > 0: every launch runs on the generic kernel (tests; OFFTB_GENERIC=1)
 void fatal_or_return(const char *where);
 
 #define OFFTB_CUDA(call)                                                                   \
@@ -116,7 +117,8 @@ struct Engine {
   bool chain_timing = false;               // stage timing of a dependent-launch chain: one event pair per chain
   std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
   std::vector<void *> peer_flags;          // every world rank's flag block as mapped here
-  void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz
+  void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz (compact per-stage tables of the power-of-two kernels)
+  void *tw_full[3] = {nullptr, nullptr, nullptr};  // exp(-2*pi*i*k/N), k < N, for the generic kernel
   Ring ring[2];
   cudaStream_t s_comp = nullptr, s_comm = nullptr, s_user = nullptr;
   bool async = false;

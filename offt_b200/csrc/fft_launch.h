@@ -37,4 +37,21 @@ cudaError_t fft_launch(int N, int prec, const FftArgs &args, long long nbatch, c
 // the same decisions without launching
 cudaError_t fft_shape(int N, int prec, const FftArgs &args, long long nbatch, FftShape *shape);
 
+// ---- any length, general block split (fft_generic.cu) ---------------------------------------------------------
+#define OFFTB_GEN_MAX_STAGES 24
+struct GenArgs {
+  FftArgs a;          // maps (with the general split), peer table, flags; a.tw = full table exp(-2*pi*i*k/N), k < N
+  int N, ns, cols;    // length, Stockham stages, columns per CTA
+  int radix[OFFTB_GEN_MAX_STAGES];
+  long long nbatch;
+};
+// factors of N in stage order; returns the stage count or -1
+int fft_generic_factor(int N, int *radix, int max_stages);
+// longest transform the shared-memory ping-pong holds
+size_t fft_generic_max_n(int prec);
+// N entries exp(-2*pi*i*k/N) as interleaved long double; returns N
+int fft_generic_twiddle_table(int N, long double *out);
+// launches (or, with shape_only, only sizes) the generic kernel; nbatch may be 0 (the launch then only waits and signals)
+cudaError_t fft_generic_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only);
+
 }  // namespace offtb

@@ -84,17 +84,22 @@ int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
   if (p < 1 || p1 < 1 || p % p1 != 0) { set_error("process grid %d = %d x ? is not a grid", p, p1); return -2; }
   const int p2 = p / p1;
   FftKernelInfo info;
-  for (int n : {Nx, Ny, Nz})
-    if (!is_pow2(n) || !fft_kernel_info(n, PREC_F64, &info)) {
-      set_error("transform length %d: only powers of two from 2 to 8192 are implemented", n);
+  for (int n : {Nx, Ny, Nz}) {
+    if (n < 1) { set_error("transform length %d", n); return -3; }
+    // powers of two up to 8192 run on the register-butterfly kernels, everything else on the generic one
+    if (!(is_pow2(n) && fft_kernel_info(n, PREC_F64, &info)) && (size_t)n > fft_generic_max_n(PREC_F64)) {
+      set_error("transform length %d: lengths that are not a power of two are limited to %zu (they run in shared memory)", n, fft_generic_max_n(PREC_F64));
       return -3;
     }
+  }
   if (p1 > OFFTB_MAX_GROUP || p2 > OFFTB_MAX_GROUP) {
     set_error("process grid %dx%d: exchange groups of more than %d ranks are not supported", p1, p2, OFFTB_MAX_GROUP);
     return -5;
   }
-  if (Nx % p1 || Ny % p1 || Ny % p2 || Nz % p2) {
-    set_error("grid %dx%dx%d does not divide evenly over %dx%d ranks (uneven splits are not implemented yet)", Nx, Ny, Nz, p1, p2);
+  // the reference's own range of P1 (params_range_setup, offt-compute.c:3005-3012): every rank owns at least one plane of
+  // each split - max(p/Nz, p/Ny, 1) <= p1 <= min(Nx, Ny, p)
+  if (p1 > Nx || p1 > Ny || p2 > Ny || p2 > Nz) {
+    set_error("grid %dx%dx%d cannot be split over %dx%d ranks (P1 outside the reference's range)", Nx, Ny, Nz, p1, p2);
     return -4;
   }
   return 0;
@@ -107,12 +112,27 @@ namespace {
 int make_twiddles(int N, int prec, void **dev) {
   std::vector<long double> tab(2 * (size_t)N + 2);
   const int count = fft_twiddle_table(N, prec, tab.data());
-  if (count < 0) { set_error("no kernel for length %d", N); return -1; }
+  if (count < 0) { *dev = nullptr; return 0; }   // not a length of the power-of-two kernels: the generic kernel has its own table
   const size_t n = (size_t)std::max(count, 1);
   std::vector<double> hd(2 * n);
   std::vector<float> hf(2 * n);
   for (size_t j = 0; j < 2 * (size_t)count; ++j) { hd[j] = (double)tab[j]; hf[j] = (float)tab[j]; }
   const size_t bytes = n * (prec == PREC_F64 ? 16 : 8);
+  OFFTB_CUDA(cudaMalloc(dev, bytes));
+  OFFTB_CUDA(cudaMemcpy(*dev, prec == PREC_F64 ? (void *)hd.data() : (void *)hf.data(), bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// full table exp(-2*pi*i*k/N) for the generic kernel
+int make_twiddles_full(int N, int prec, void **dev) {
+  *dev = nullptr;
+  if ((size_t)N > fft_generic_max_n(prec)) return 0;   // a length only the power-of-two kernels take
+  std::vector<long double> tab(2 * (size_t)N);
+  fft_generic_twiddle_table(N, tab.data());
+  std::vector<double> hd(2 * (size_t)N);
+  std::vector<float> hf(2 * (size_t)N);
+  for (size_t j = 0; j < 2 * (size_t)N; ++j) { hd[j] = (double)tab[j]; hf[j] = (float)tab[j]; }
+  const size_t bytes = (size_t)N * (prec == PREC_F64 ? 16 : 8);
   OFFTB_CUDA(cudaMalloc(dev, bytes));
   OFFTB_CUDA(cudaMemcpy(*dev, prec == PREC_F64 ? (void *)hd.data() : (void *)hf.data(), bytes, cudaMemcpyHostToDevice));
   return 0;
@@ -126,6 +146,17 @@ FftMap mk_map(long long off, long long nlo_count, long long n_hi, long long n_lo
   m.n_hi = n_hi; m.n_lo = n_lo;
   m.B0 = (unsigned)std::max<long long>(B0, 1); m.B1 = (unsigned)std::max<long long>(B1, 1);
   m.s0 = s0; m.s1 = s1; m.s2 = s2;
+  m.gF = m.gb = m.gg = 0;
+  return m;
+}
+
+// The transform index of `m` is divided among `owners` blocks the way the reference divides an axis among ranks
+// (offt-compute.c:128-144): floor(N/owners) items each, the last N % owners blocks one more.  Even divisions into
+// power-of-two blocks keep the shift/mask split the fast kernels use; everything else takes the general split.
+FftMap split_over(FftMap m, long long N, long long owners) {
+  const long long F = N / owners, b = N % owners, M = F + (b ? 1 : 0);
+  if (b == 0 && is_pow2(M)) { m.n_lg = lg2(M); m.gg = 0; }
+  else { m.n_lg = 30; m.gF = (int)F; m.gb = (int)b; m.gg = (int)owners; }
   return m;
 }
 
@@ -202,9 +233,11 @@ bool bulk_store_ok(const Engine &E, const FftArgs &a, int N) {
 }
 
 int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
-  if (L.nbatch <= 0) return 0;
+  // a launch with nothing to transform still has to take part in the flag protocol of its tile
+  if (L.nbatch <= 0 && L.signal_count == 0) return 0;
+  if (L.nbatch < 0) L.nbatch = 0;
   FftKernelInfo info;
-  if (!fft_kernel_info(L.N, E.prec, &info)) { set_error("no kernel for length %d", L.N); return -1; }
+  const bool generic = g_force_generic > 0 || L.nbatch == 0 || L.im.gg > 0 || L.om.gg > 0 || !fft_kernel_info(L.N, E.prec, &info);
   if (L.nbatch >= (1LL << 32)) { set_error("batch of %lld rows exceeds the 32-bit batch index", L.nbatch); return -1; }
   FftArgs a;
   memset(&a, 0, sizeof(a));
@@ -213,7 +246,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
     std::swap(L.load_cfast, L.store_cfast);
     const void *t = L.in; L.in = L.out; L.out = const_cast<void *>(t);
   }
-  a.in = L.in; a.out = L.out; a.tw = E.tw[L.axis];
+  a.in = L.in; a.out = L.out; a.tw = generic ? E.tw_full[L.axis] : E.tw[L.axis];
   a.im = L.im; a.om = L.om;
   a.load_cfast = L.load_cfast; a.store_cfast = L.store_cfast;
   a.conj = inverse ? 1 : 0;
@@ -224,6 +257,23 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done_counter;
   a.grid_cap = L.grid_cap;
   a.wait_timeout_ns = E.wait_timeout_ns; a.error_word = E.d_error;
+  if (generic) {
+    // any length, uneven splits (fft_generic.cu)
+    if (!a.tw) { set_error("length %d with this split needs the generic kernel, which holds at most %zu points", L.N, fft_generic_max_n(E.prec)); return -1; }
+    if (E.dry_shape) {
+      cudaError_t se = fft_generic_launch(L.N, E.prec, a, L.nbatch, st, E.dry_shape);
+      if (se != cudaSuccess) { set_error("generic kernel shape (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(se)); return -1; }
+      return 0;
+    }
+    cudaEvent_t g0 = nullptr, g1 = nullptr;
+    const bool gtimed = E.stage_timing && !E.chain_timing;
+    if (gtimed) { g0 = pool_event(E); g1 = pool_event(E); cudaEventRecord(g0, st); }
+    cudaError_t ge = fft_generic_launch(L.N, E.prec, a, L.nbatch, st, nullptr);
+    if (ge != cudaSuccess) { set_error("generic kernel launch (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(ge)); return -1; }
+    if (gtimed) { cudaEventRecord(g1, st); E.timed.push_back({stage, {g0, g1}}); }
+    E.launches++;
+    return 0;
+  }
   a.pdl = L.pdl;
   a.c_log = pick_c_log(E, info, L);
   a.bulk_store = bulk_store_ok(E, a, L.N) ? 1 : 0;
@@ -279,7 +329,7 @@ Launch L_fftz_local(const Dims &d, const void *in, void *out, long long x0, long
 Launch L_k1(const Dims &d, const void *U, void *send, long long x0, long long myT) {
   Launch L = L_fftz_local(d, U, send, x0, myT);
   // z splits into (destination, z_local): block a at a*myT*M2*M3, inside it [x][y][z_local]
-  L.om = mk_map(0, d.M3, myT * d.M2 * d.M3, 1, d.m2, d.M3, myT, d.M2 * d.M3, 0);
+  L.om = split_over(mk_map(0, d.M3, myT * d.M2 * d.M3, 1, d.m2, d.M3, myT, d.M2 * d.M3, 0), d.Nz, d.p2);
   return L;
 }
 
@@ -288,7 +338,7 @@ Launch L_k2(const Dims &d, const void *recv, void *A, long long x0, long long my
   Launch L;
   L.N = (int)d.Ny; L.axis = 1; L.in = recv; L.out = A;
   // y splits into (source, y_local): block a holds [x][y_local][z]
-  L.im = mk_map(0, d.M2, myT * d.M2 * d.M3, d.M3, d.m3, 1, myT, d.M2 * d.M3, 0);
+  L.im = split_over(mk_map(0, d.M2, myT * d.M2 * d.M3, d.M3, d.m3, 1, myT, d.M2 * d.M3, 0), d.Ny, d.p2);
   L.om = mk_map(x0 * d.dX, 0, 0, d.dY, d.m3, 1, myT, d.dX, 0);
   L.nbatch = d.m3 * myT; L.load_cfast = L.store_cfast = true;
   return L;
@@ -314,7 +364,7 @@ Launch L_k3(const Engine &E, const Dims &d, const void *A, void *send, long long
   L.N = (int)d.Ny; L.axis = 1; L.in = A; L.out = send;
   L.im = mk_map(z0, 0, 0, d.dY, cz, 1, myT / cz, cz, d.dX);
   // y splits into (destination, y_local): block a holds [x][z_hi][y_local][z_lo]
-  L.om = mk_map(0, d.M4, d.M1 * d.M4 * myT, cz, cz, 1, myT / cz, d.M4 * cz, myT * d.M4);
+  L.om = split_over(mk_map(0, d.M4, d.M1 * d.M4 * myT, cz, cz, 1, myT / cz, d.M4 * cz, myT * d.M4), d.Ny, d.p1);
   L.nbatch = myT * d.m1; L.load_cfast = L.store_cfast = true;
   return L;
 }
@@ -325,7 +375,7 @@ Launch L_k4(const Engine &E, const Dims &d, const void *recv, void *U, long long
   const long long cz = z_chunk(E, myT);
   L.N = (int)d.Nx; L.axis = 0; L.in = recv; L.out = U;
   // x splits into (source, x_local): block a holds [x_local][z_hi][y][z_lo]; batch digits (z_lo, y, z_hi)
-  L.im = mk_map(0, d.M1, d.M1 * d.M4 * myT, myT * d.M4, cz, 1, d.m4, cz, d.M4 * cz);
+  L.im = split_over(mk_map(0, d.M1, d.M1 * d.M4 * myT, myT * d.M4, cz, 1, d.m4, cz, d.M4 * cz), d.Nx, d.p1);
   L.om = mk_map(z0 * d.os2, 0, 0, d.os0, cz, d.os2, d.m4, d.os1, cz * d.os2);
   L.nbatch = myT * d.m4; L.load_cfast = true; L.store_cfast = (d.os2 == 1);
   return L;
@@ -395,10 +445,12 @@ long long block_elems(const Dims &d, int phase, long long myT) {
 
 // One tile's all-to-all.  `from`/`to` are ring slots: forward sends `send` -> peers' `recv`,
 // the backward transform runs the same exchange from `recv` to `send`.
-int exchange(std::vector<Engine *> &engs, int phase, int slot, long long myT, bool inverse, cudaStream_t st) {
+int exchange(std::vector<Engine *> &engs, int phase, int slot, const std::vector<long long> &tile_T, bool inverse, cudaStream_t st) {
   World &w = world();
-  for (Engine *Ep : engs) {
-    Engine &E = *Ep;
+  for (size_t ke = 0; ke < engs.size(); ++ke) {
+    Engine &E = *engs[ke];
+    const long long myT = tile_T[ke];
+    if (myT <= 0) continue;   // this rank's group has no such tile (uneven division: groups differ in their plane counts)
     const Dims d = dims_of(E.po);
     const long long blk = block_elems(d, phase, myT);
     std::vector<int> members;
@@ -597,14 +649,22 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
 int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, bool inverse) {
   Engine &E0 = *engs[0];
   const Dims d0 = dims_of(E0.po);
-  const long long planes = phase == 1 ? d0.m1 : d0.m3;              // :3529, :3710
   const int tiling = phase == 1 ? d0.T1 : d0.T2;
   const int W = phase == 1 ? d0.W1 : d0.W2;
-  const int blocks = (int)((planes + tiling - 1) / tiling);
+  // planes of the tiled axis: the same for all members of an exchange group, but with an uneven division not for all
+  // groups (offt-compute.c:3529, 3710 use the rank's own m1 / m3), so emulated-rank worlds count per plan
+  std::vector<long long> planes(engs.size());
+  int blocks = 0;
+  for (size_t k = 0; k < engs.size(); ++k) {
+    const Dims dk = dims_of(engs[k]->po);
+    planes[k] = phase == 1 ? dk.m1 : dk.m3;
+    blocks = std::max(blocks, (int)((planes[k] + tiling - 1) / tiling));
+  }
   Ring &R0 = E0.ring[phase - 1];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
   const bool fused = E0.xmode == XCHG_FUSED;
-  auto tile_T = [&](int i) { return i == blocks - 1 ? planes - (long long)(blocks - 1) * tiling : (long long)tiling; };
+  auto tile_Tk = [&](size_t k, int i) { return std::max<long long>(0, std::min<long long>(tiling, planes[k] - (long long)i * tiling)); };
+  auto tile_T = [&](int i) { return tile_Tk(0, i); };
   // fused exchange between processes: readers on the second stream, ordered against the writers by flags alone
   bool two = false;
   if (fused && !world().local && blocks > 1) {
@@ -641,39 +701,45 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   cudaEvent_t ce[4] = {nullptr, nullptr, nullptr, nullptr};
   E0.chain_timing = pdl && E0.stage_timing;
   if (E0.chain_timing) for (cudaEvent_t &e : ce) e = pool_event(E0);
-  auto first = [&](Engine &E, const Bufs &b, int i) {
+  auto first = [&](size_t k, int i) {
+    Engine &E = *engs[k];
+    if (tile_Tk(k, i) <= 0) return 0;
     E.pdl_next = pdl ? (1 | (n_first ? 2 : 0)) : 0;
     if (E.chain_timing && !n_first) cudaEventRecord(ce[0], sc);
     ++n_first;
-    return inverse ? consume(engs, E, b, phase, i, tile_T(i), true, sc) : produce(engs, E, b, phase, i, tile_T(i), false, sc);
+    return inverse ? consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, sc) : produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, sc);
   };
-  auto second = [&](Engine &E, const Bufs &b, int i) {
+  auto second = [&](size_t k, int i) {
+    Engine &E = *engs[k];
+    if (tile_Tk(k, i) <= 0) return 0;
     E.pdl_next = pdl ? (1 | (n_second ? 2 : 0)) : 0;
     if (E.chain_timing && !n_second) cudaEventRecord(ce[2], s2);
     ++n_second;
-    return inverse ? produce(engs, E, b, phase, i, tile_T(i), true, s2) : consume(engs, E, b, phase, i, tile_T(i), false, s2);
+    return inverse ? produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, s2) : consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, s2);
   };
+  std::vector<long long> tts(engs.size());
   for (int i = 0; i < blocks; ++i) {
     const int slot = slot_of(R0, i);
     for (size_t k = 0; k < engs.size(); ++k)
-      if (first(*engs[k], bufs[k], i)) return -1;
+      if (first(k, i)) return -1;
     if (!fused) {
       OFFTB_CUDA(cudaEventRecord(R0.packed[slot], sc));
       OFFTB_CUDA(cudaStreamWaitEvent(sx, R0.packed[slot], 0));
-      if (exchange(engs, phase, slot, tile_T(i), inverse, sx)) return -1;
+      for (size_t k = 0; k < engs.size(); ++k) tts[k] = tile_Tk(k, i);
+      if (exchange(engs, phase, slot, tts, inverse, sx)) return -1;
       OFFTB_CUDA(cudaEventRecord(R0.recvd[slot], sx));
     }
     if (i >= W) {
       const int j = i - W;
       if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
       for (size_t k = 0; k < engs.size(); ++k)
-        if (second(*engs[k], bufs[k], j)) return -1;
+        if (second(k, j)) return -1;
     }
   }
   for (int j = std::max(blocks - W, 0); j < blocks; ++j) {
     if (!fused) OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[slot_of(R0, j)], 0));
     for (size_t k = 0; k < engs.size(); ++k)
-      if (second(*engs[k], bufs[k], j)) return -1;
+      if (second(k, j)) return -1;
   }
   if (E0.chain_timing) {
     // one event pair per chain: the span from the first launch's start to the last launch's end, flag waits included
@@ -767,7 +833,7 @@ int engine_create(struct _offt_plan *po) {
   E->alloc = alloc_elems(po->Nx, po->Ny, po->Nz, po->p, c->p1);
   const int Ns[3] = {po->Nx, po->Ny, po->Nz};
   for (int a = 0; a < 3; ++a)
-    if (make_twiddles(Ns[a], E->prec, &E->tw[a])) return -1;
+    if (make_twiddles(Ns[a], E->prec, &E->tw[a]) || make_twiddles_full(Ns[a], E->prec, &E->tw_full[a])) return -1;
   OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comp, cudaStreamNonBlocking));
   OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comm, cudaStreamNonBlocking));
   OFFTB_CUDA(cudaEventCreate(&E->ev_begin));
@@ -864,7 +930,7 @@ void engine_destroy(struct _offt_plan *po) {
   cudaFree(E->d_flags);
   if (E->h_error) cudaFreeHost(E->h_error);
   if (E->registered_host) cudaHostUnregister(E->registered_host);
-  for (int a = 0; a < 3; ++a) cudaFree(E->tw[a]);
+  for (int a = 0; a < 3; ++a) { cudaFree(E->tw[a]); cudaFree(E->tw_full[a]); }
   cudaFree(E->d_user); cudaFree(E->d_scratch); cudaFree(E->d_ring);
   free_ring(E->ring[0]); free_ring(E->ring[1]);
   for (cudaEvent_t e : E->event_pool) cudaEventDestroy(e);

@@ -29,9 +29,11 @@ P = ob.P
 def cases(p):
     out = [((64, 32, 128), 1, {P.P1: p}, 64), ((64, 32, 128), 1, {P.P1: 1}, 64), ((64, 64, 64), 1, {P.P1: p, P.S: 1, P.T2: 8, P.W2: 3}, 64),
            ((32, 64, 64), 1, {P.P1: 1, P.S: 1, P.T1: 5, P.W1: 1}, 64), ((256, 256, 256), 1, {P.P1: p, P.S: 1}, 64),
-           ((128, 64, 64), 1, {P.P1: p}, 32)]
+           ((128, 64, 64), 1, {P.P1: p}, 32),
+           # lengths with odd factors and uneven splits: the any-length kernel and the general block split between real ranks
+           ((15, 10, 9), 1, {P.P1: p, P.V: 3, P.T2: 2}, 64), ((27, 20, 45), 1, {P.P1: 1, P.S: 1, P.T1: 4}, 64)]
     if p >= 4:
-        out += [((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.Ry: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
+        out += [((10, 9, 15), 0, {P.P1: 2, P.V: 3, P.T1: 2, P.T2: 3}, 64), ((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.Ry: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
     return out
 
 

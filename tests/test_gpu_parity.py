@@ -139,7 +139,7 @@ def test_plan_matches_oracle(oracle, N, p, oned, eq, custom):
     assert O.rel_l2(rt, grid) < 1e-12
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("uneven")])
+@pytest.mark.parametrize("name", golden_names())
 def test_plan_matches_reference_fixture(name):
     """fixtures = outputs of the unmodified reference (tests/golden/make_golden.py)"""
     _torch()
@@ -209,12 +209,103 @@ def test_unsupported_inputs_fail_loudly():
     import offt_b200 as ob
     with local_world(1):
         with pytest.raises(ob.OfftError):
-            ob.Plan(12, 10, 9, custom={P.P1: 1})            # not powers of two
+            ob.Plan(16, 16, 7001, custom={P.P1: 1})         # not a power of two and too long for the shared-memory kernel
         with pytest.raises(ob.OfftError):
-            ob.Plan(16, 16, 16, is_r2c=1, custom={P.P1: 1})  # r2c not implemented
-    with local_world(3):
+            ob.Plan(16, 16, 16384, custom={P.P1: 1})        # power of two beyond the kernels
+    with local_world(4):
         with pytest.raises(ob.OfftError):
-            ob.Plan(16, 16, 16, custom={P.P1: 3}, rank=0)   # uneven split
+            ob.Plan(2, 16, 16, custom={P.P1: 4}, rank=0)    # P1 outside the reference's range: a rank without an x plane
+
+
+# ---------------------------------------------------------------- any length, uneven splits (fft_generic.cu)
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("n", [1, 3, 5, 6, 7, 9, 10, 12, 15, 18, 20, 49, 60, 100, 121, 127, 210, 243, 360, 1000, 1001, 1536, 2187, 3000])
+def test_rows_any_length(oracle, n, bits):
+    """lengths with odd factors and primes, contiguous and strided, forward and backward (the reference hands any
+    length to FFTW, offt-compute.c:338, 416, 443)"""
+    torch = _torch()
+    import offt_b200 as ob
+    rng = np.random.default_rng(n)
+    rows = 12
+    a = (rng.uniform(-1, 1, (rows, n)) + 1j * rng.uniform(-1, 1, (rows, n)))
+    want = np.fft.fft(a, axis=1)
+    chk = a[:2].copy()
+    oracle.dft_rows(chk, n, 1, n, 2, -1)        # the oracle's own 1-D arithmetic agrees with numpy on this length
+    assert O.rel_l2(chk, want[:2]) < 1e-12
+    cdt = torch.complex128 if bits == 64 else torch.complex64
+    with local_world(1):
+        d = torch.from_numpy(a).to("cuda").to(cdt).contiguous()
+        ob.fft_rows(d, n, 1, n, rows, sign=-1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy(), want) < TOL[bits]
+        d = torch.from_numpy(np.ascontiguousarray(a.T)).to("cuda").to(cdt).contiguous()
+        ob.fft_rows(d, n, rows, 1, rows, sign=-1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy().T, want) < TOL[bits]
+        ob.fft_rows(d, n, rows, 1, rows, sign=+1, bits=bits)
+        assert O.rel_l2(d.cpu().numpy().T / n, a) < TOL[bits]
+
+
+UNEVEN_CASES = [
+    # N, p, is_oned, is_equalxy, custom: non-power-of-two grids, uneven process grids, exact-count bits of _V_
+    ((12, 10, 9), 1, 0, 0, {P.P1: 1}),
+    ((12, 10, 9), 1, 0, 0, {P.P1: 1, P.S: 1}),
+    ((12, 10, 9), 4, 0, 0, {P.P1: 2, P.V: 3}),
+    ((12, 10, 9), 4, 0, 0, {P.P1: 2, P.V: 0, P.S: 1}),
+    ((12, 10, 9), 3, 1, 0, {P.P1: 3, P.V: 3, P.T2: 2}),
+    ((12, 10, 9), 3, 1, 0, {P.P1: 1, P.V: 1, P.T1: 5}),
+    ((20, 12, 18), 6, 0, 0, {P.P1: 3, P.V: 3, P.T1: 3, P.T2: 4}),
+    ((20, 12, 18), 6, 0, 0, {P.P1: 2, P.V: 2, P.S: 1, P.RY: 3}),
+    ((16, 16, 16), 3, 0, 0, {P.P1: 3}),                         # power-of-two lengths, uneven split
+    ((16, 32, 16), 6, 0, 0, {P.P1: 2, P.T1: 3, P.T2: 2}),
+    ((18, 18, 6), 4, 0, 1, {P.P1: 2}),                          # equalxy with odd-factor lengths
+    ((30, 42, 70), 5, 1, 0, {P.P1: 5, P.S: 1}),
+    ((30, 42, 70), 7, 1, 0, {P.P1: 1}),
+    ((96, 80, 48), 8, 0, 0, {P.P1: 4, P.T1: 5, P.T2: 7, P.W1: 2, P.W2: 1}),
+]
+
+
+@pytest.mark.parametrize("N,p,oned,eq,custom", UNEVEN_CASES)
+def test_uneven_and_any_length_plans_match_oracle(oracle, N, p, oned, eq, custom):
+    _torch()
+    grid = O.grid_values(6, *N)
+    v = oracle.resolve_params(*N, p, custom)
+    want = oracle.execute(grid, p, v, oned, eq)
+    got, launches, back = gpu_forward(grid, p, custom, oned, eq, inverse_too=True)
+    assert launches > 0
+    for a, b in zip(got, want):
+        assert a.params == b.params
+        assert (a.istart, a.isize, a.istride, a.ostart, a.osize, a.ostride, a.alloc) == \
+               (b.istart, b.isize, b.istride, b.ostart, b.osize, b.ostride, b.alloc)
+    A, B = O.gather_output(got), O.gather_output(want)
+    assert not np.isnan(A).any()
+    assert O.rel_l2(A, B) < 1e-12 and O.rel_l2(A, np.fft.fftn(grid)) < 1e-12
+    assert O.rel_l2(gather_input(got, back) / np.prod(N), grid) < 1e-12
+
+
+@pytest.mark.parametrize("N,p,oned,eq,custom", [CASES[i] for i in (0, 4, 9, 11, 15, 16, 19)])
+def test_generic_kernel_on_power_of_two_plans(oracle, N, p, oned, eq, custom):
+    """the any-length kernel forced onto plans the fast kernels normally take: same results"""
+    _torch()
+    import offt_b200 as ob
+    grid = O.grid_values(5, *N)
+    want = O.gather_output(oracle.execute(grid, p, oracle.resolve_params(*N, p, custom), oned, eq))
+    ob.set_force_generic(True)
+    try:
+        got, launches, back = gpu_forward(grid, p, custom, oned, eq, inverse_too=True)
+    finally:
+        ob.set_force_generic(False)
+    assert launches > 0
+    assert O.rel_l2(O.gather_output(got), want) < 1e-12
+    assert O.rel_l2(gather_input(got, back) / np.prod(N), grid) < 1e-12
+
+
+def test_uneven_single_precision(oracle):
+    _torch()
+    N, p, custom = (20, 12, 18), 6, {P.P1: 3, P.V: 3}
+    grid = O.grid_values(9, *N)
+    want = O.gather_output(oracle.execute(grid, p, oracle.resolve_params(*N, p, custom), 0, 0))
+    got, _, back = gpu_forward(grid, p, custom, 0, 0, bits=32, inverse_too=True)
+    assert O.rel_l2(O.gather_output(got, np.complex64), want) < 1e-5
+    assert O.rel_l2(gather_input(got, back, np.complex64) / np.prod(N), grid) < 1e-5
 
 
 def test_async_execution_on_the_callers_stream(oracle):
