@@ -53,6 +53,7 @@ int offtb_plan_set_async(struct _offt_plan *po, int is_async);
 /* complex elements the caller's in-place array must hold (run-fft.c:294-304, 64-bit) */
 long long offtb_plan_alloc_elems(const struct _offt_plan *po);
 long long offtb_alloc_elems(int Nx, int Ny, int Nz, int p, int p1);
+long long offtb_alloc_elems_r2c(int Nx, int Ny, int Nz, int p, int p1, int is_r2c);   /* run-fft.c:296-300 with M3 from Nz/2+1 */
 /* kernels launched / milliseconds on the device by the last execute of this plan */
 int offtb_plan_last_launches(const struct _offt_plan *po);
 double offtb_plan_last_ms(const struct _offt_plan *po);
@@ -91,6 +92,8 @@ void offtb_params_adjust(int Nx, int Ny, int Nz, int p, int is_oned, int *v24);
 void offtb_params_range(int Nx, int Ny, int Nz, int p, int *lists, int stride, int *sizes);
 /* rank-local box for (p, p1, rank) without creating a plan */
 int offtb_comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy);
+/* the same for real-to-complex plans (is_r2c: Nz/2+1 complex points per z row, offt-compute.c:63) */
+int offtb_comm_fill_r2c(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy, int is_r2c);
 /* 0 if the library can run this problem, else a negative code (message in offtb_last_error) */
 int offtb_check_supported(int Nx, int Ny, int Nz, int p, int p1);
 /* exchange bookkeeping of one tile: blocks per peer in complex elements (phase 1 or 2) */

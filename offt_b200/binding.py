@@ -95,6 +95,9 @@ def _load():
     L.offtb_params_range.restype = None
     L.offtb_params_range.argtypes = [i] * 4 + [C.POINTER(i), i, C.POINTER(i)]
     L.offtb_comm_fill.argtypes = [C.POINTER(OfftComm)] + [i] * 8
+    L.offtb_comm_fill_r2c.argtypes = [C.POINTER(OfftComm)] + [i] * 9
+    L.offtb_alloc_elems_r2c.restype = ll
+    L.offtb_alloc_elems_r2c.argtypes = [i] * 6
     L.offtb_check_supported.argtypes = [i] * 5
     L.offtb_tune.argtypes = [C.POINTER(OfftPlan), vp, vp, i, i]
     L.offtb_set_exit_on_error(0)   # Python raises instead of exit(-1)
@@ -317,16 +320,16 @@ def params_adjust(Nx, Ny, Nz, p, is_oned, v) -> list:
     return list(vv)
 
 
-def comm_box(Nx, Ny, Nz, p, p1, rank, S=0, is_equalxy=0) -> dict:
+def comm_box(Nx, Ny, Nz, p, p1, rank, S=0, is_equalxy=0, is_r2c=0) -> dict:
     c = OfftComm()
-    _check(lib.offtb_comm_fill(C.byref(c), Nx, Ny, Nz, p, p1, rank, S, is_equalxy), "offtb_comm_fill")
+    _check(lib.offtb_comm_fill_r2c(C.byref(c), Nx, Ny, Nz, p, p1, rank, S, is_equalxy, is_r2c), "offtb_comm_fill")
     d = {k: getattr(c, k) for k in "p1 p2 M1 M2 M3 M4 F1 F2 F3 F4 m1 m2 m3 m4 b1 b2 b3 b4".split()}
     d.update({k: tuple(getattr(c, k)) for k in "istart isize istride ostart osize ostride".split()})
     return d
 
 
-def alloc_elems(Nx, Ny, Nz, p, p1) -> int:
-    return int(lib.offtb_alloc_elems(Nx, Ny, Nz, p, p1))
+def alloc_elems(Nx, Ny, Nz, p, p1, is_r2c=0) -> int:
+    return int(lib.offtb_alloc_elems_r2c(Nx, Ny, Nz, p, p1, is_r2c))
 
 
 def check_supported(Nx, Ny, Nz, p, p1) -> tuple:

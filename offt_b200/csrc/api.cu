@@ -44,7 +44,7 @@ extern "C" {
 
 struct _offt_comm *offt_comm_malloc(struct _offt_plan *po) {
   struct _offt_comm *c = (struct _offt_comm *)calloc(1, sizeof(struct _offt_comm));
-  comm_fill(c, po->Nx, po->Ny, po->Nz, po->p, po->params->v[_P1_], po->rank, po->params->v[_S_], po->is_equalxy);
+  comm_fill(c, po->Nx, po->Ny, po->Nz, po->p, po->params->v[_P1_], po->rank, po->params->v[_S_], po->is_equalxy, po->is_r2c);
   return c;
 }
 
@@ -56,7 +56,14 @@ int offtb_comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1,
   return 0;
 }
 
+int offtb_comm_fill_r2c(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy, int is_r2c) {
+  if (p < 1 || p1 < 1 || p % p1 || rank < 0 || rank >= p) { set_error("bad process grid"); return -1; }
+  comm_fill(c, Nx, Ny, Nz, p, p1, rank, S, is_equalxy, is_r2c);
+  return 0;
+}
+
 long long offtb_alloc_elems(int Nx, int Ny, int Nz, int p, int p1) { return alloc_elems(Nx, Ny, Nz, p, p1); }
+long long offtb_alloc_elems_r2c(int Nx, int Ny, int Nz, int p, int p1, int is_r2c) { return alloc_elems(Nx, Ny, Nz, p, p1, is_r2c); }
 int offtb_check_supported(int Nx, int Ny, int Nz, int p, int p1) { return check_supported(Nx, Ny, Nz, p, p1); }
 
 struct _offt_plan *offt_3d_init(int Nx, int Ny, int Nz, double *in, double *out, int is_r2c, int fftw_flag,
@@ -79,7 +86,8 @@ struct _offt_plan *offt_3d_init(int Nx, int Ny, int Nz, double *in, double *out,
   po->extrapolation_window = extrapolation_window;
   po->params = (struct _offt_params *)calloc(1, sizeof(struct _offt_params));
   // defaults on the value grid, then the caller's non-negative overrides (which need not be on it)
-  params_default(Nx, Ny, Nz, po->p, is_W0, is_notest, po->params->v);
+  // real-to-complex plans size every z-related tunable by the Nz/2+1 complex points that remain (offt-compute.c:3008, 3045, 3141)
+  params_default(Nx, Ny, is_r2c ? Nz / 2 + 1 : Nz, po->p, is_W0, is_notest, po->params->v);
   po->params->is_converged = 1;
   if (!po->rank) print_params(po->params->v);
   if (custom_params)

@@ -65,9 +65,9 @@ void params_adjust(int Nx, int Ny, int Nz, int p, int is_oned, int *v);
 const char *param_name(int i);
 
 // ---- layout (plan.cu) ---------------------------------------------------------------------
-void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy);
-long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1);
-int check_supported(int Nx, int Ny, int Nz, int p, int p1);
+void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy, int is_r2c = 0);
+long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1, int is_r2c = 0);
+int check_supported(int Nx, int Ny, int Nz, int p, int p1, int is_r2c = 0);
 
 enum Schedule { SCHED_SINGLE, SCHED_SLAB_1XP, SCHED_SLAB_PX1, SCHED_PENCIL };
 enum StageId { ST_K1, ST_K2, ST_K3, ST_K4, ST_X1, ST_X2, ST_H2D, ST_D2H, ST_COUNT };

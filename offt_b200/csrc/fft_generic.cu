@@ -53,14 +53,36 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     const int ncol = (int)(g.nbatch - b0 < C ? g.nbatch - b0 : C);
     const int total = ncol * N;
     // ---- load [column][n]
-    for (int e = tid; e < total; e += nthreads) {
-      int c, n;
-      if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { n = e % N; c = e / N; }
-      int blk, lo;
-      split_n(a.im, n, blk, lo);
-      cx<T> v = ((const cx<T> *)a.in)[map_b(a.im, (unsigned)(b0 + c)) + (long long)blk * a.im.n_hi + (long long)lo * a.im.n_lo];
-      v.y *= cj;
-      buf0[c * N + n] = v;
+    const int Nh = N / 2 + 1;
+    if (a.real_mode == 1) {
+      // rows of N real numbers in the in-place r2c layout: real n of the row that starts at complex offset o is double 2*o + n
+      for (int e = tid; e < total; e += nthreads) {
+        const int n = e % N, c = e / N;
+        const T re = ((const T *)a.in)[2 * map_b(a.im, (unsigned)(b0 + c)) + n];
+        buf0[c * N + n] = cx<T>{re, (T)0};
+      }
+    } else if (a.real_mode == 2) {
+      // N/2+1 complex points per row, completed to the Hermitian row X[N-n] = conj(X[n])
+      for (int e = tid; e < ncol * Nh; e += nthreads) {
+        int c, n;
+        if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { n = e % Nh; c = e / Nh; }
+        int blk, lo;
+        split_n(a.im, n, blk, lo);
+        cx<T> v = ((const cx<T> *)a.in)[map_b(a.im, (unsigned)(b0 + c)) + (long long)blk * a.im.n_hi + (long long)lo * a.im.n_lo];
+        v.y *= cj;
+        buf0[c * N + n] = v;
+        if (n > 0 && 2 * n != N) buf0[c * N + N - n] = cx<T>{v.x, -v.y};
+      }
+    } else {
+      for (int e = tid; e < total; e += nthreads) {
+        int c, n;
+        if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { n = e % N; c = e / N; }
+        int blk, lo;
+        split_n(a.im, n, blk, lo);
+        cx<T> v = ((const cx<T> *)a.in)[map_b(a.im, (unsigned)(b0 + c)) + (long long)blk * a.im.n_hi + (long long)lo * a.im.n_lo];
+        v.y *= cj;
+        buf0[c * N + n] = v;
+      }
     }
     __syncthreads();
     // ---- Stockham stages
@@ -95,14 +117,22 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
       Ns *= R;
     }
     // ---- store
-    for (int e = tid; e < total; e += nthreads) {
-      int c, n;
-      if (a.store_cfast) { c = e % ncol; n = e / ncol; } else { n = e % N; c = e / N; }
-      int blk, lo;
-      split_n(a.om, n, blk, lo);
-      cx<T> v = src[c * N + n];
-      v.y *= cj;
-      ((cx<T> *)s_tab[blk])[map_b(a.om, (unsigned)(b0 + c)) + (long long)lo * a.om.n_lo] = v;
+    if (a.real_mode == 2) {
+      for (int e = tid; e < total; e += nthreads) {
+        const int n = e % N, c = e / N;
+        ((T *)s_tab[0])[2 * map_b(a.om, (unsigned)(b0 + c)) + n] = src[c * N + n].x;
+      }
+    } else {
+      const int Nst = a.real_mode == 1 ? Nh : N;   // a real row's spectrum is stored up to the Nyquist point only
+      for (int e = tid; e < ncol * Nst; e += nthreads) {
+        int c, n;
+        if (a.store_cfast) { c = e % ncol; n = e / ncol; } else { n = e % Nst; c = e / Nst; }
+        int blk, lo;
+        split_n(a.om, n, blk, lo);
+        cx<T> v = src[c * N + n];
+        v.y *= cj;
+        ((cx<T> *)s_tab[blk])[map_b(a.om, (unsigned)(b0 + c)) + (long long)lo * a.om.n_lo] = v;
+      }
     }
     __syncthreads();
   }

@@ -109,6 +109,10 @@ struct FftArgs {
   // the CTA works on the next tile in the next slot.  Needs a ring of >= 2 slots; 3 keeps one tile landing, one
   // in the butterflies and one draining.  Set by the host when the store map allows it (fft_inst.cu, plan_one).
   int bulk_store;
+  // z pass of a real-to-complex plan (fft_generic.cu only).  1: the input rows are N real numbers (the in-place r2c
+  // layout, run-fft.c:53-55: double index 2*row_start + n) and only outputs 0..N/2 are stored; 2: the backward
+  // transform of that - N/2+1 complex points in, completed to the Hermitian row, N real numbers out.
+  int real_mode;
 };
 
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }

@@ -49,10 +49,13 @@ int lg2(long long n) { int l = 0; while ((1LL << l) < n) ++l; return l; }
 
 }  // namespace
 
-void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy) {
+void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy, int is_r2c) {
   const int p2 = p / p1;
   const int rx = rank / p2, ry = rank % p2;   // rank -> (row, column) of the process grid
-  const Share x1 = share_of(Nx, p1, rx), y2 = share_of(Ny, p2, ry), z2 = share_of(Nz, p2, ry), y1 = share_of(Ny, p1, rx);
+  // real-to-complex plans keep Nz/2+1 complex points of every z row: that count replaces Nz in everything but the
+  // input box's z extent (offt-compute.c:63, 130-143, 251)
+  const int Nzc = is_r2c ? Nz / 2 + 1 : Nz;
+  const Share x1 = share_of(Nx, p1, rx), y2 = share_of(Ny, p2, ry), z2 = share_of(Nzc, p2, ry), y1 = share_of(Ny, p1, rx);
   c->p1 = p1; c->p2 = p2;
   c->comm1 = c->comm2 = nullptr; c->group1 = c->group2 = nullptr;
   c->M1 = x1.ceil; c->M2 = y2.ceil; c->M3 = z2.ceil; c->M4 = y1.ceil;
@@ -73,16 +76,20 @@ void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int 
   else { c->ostride[0] = 1; c->ostride[1] = xrow; c->ostride[2] = xrow * c->M4; }                          // z-y-x
 }
 
-long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1) {
+long long alloc_elems(int Nx, int Ny, int Nz, int p, int p1, int is_r2c) {
   const int p2 = p / p1;
   auto cd = [](long long a, long long b) { return (a + b - 1) / b; };
-  const long long M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(Nz, p2), M4 = cd(Ny, p1);
+  const long long M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(is_r2c ? Nz / 2 + 1 : Nz, p2), M4 = cd(Ny, p1);   // run-fft.c:296-300
   return std::max(M2 * p2, M4 * p1) * M1 * M3;
 }
 
-int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
+int check_supported(int Nx, int Ny, int Nz, int p, int p1, int is_r2c) {
   if (p < 1 || p1 < 1 || p % p1 != 0) { set_error("process grid %d = %d x ? is not a grid", p, p1); return -2; }
   const int p2 = p / p1;
+  if (is_r2c && (size_t)Nz > fft_generic_max_n(PREC_F64)) {
+    set_error("real-to-complex plans transform z in shared memory: Nz = %d exceeds %zu", Nz, fft_generic_max_n(PREC_F64));
+    return -3;
+  }
   FftKernelInfo info;
   for (int n : {Nx, Ny, Nz}) {
     if (n < 1) { set_error("transform length %d", n); return -3; }
@@ -98,7 +105,7 @@ int check_supported(int Nx, int Ny, int Nz, int p, int p1) {
   }
   // the reference's own range of P1 (params_range_setup, offt-compute.c:3005-3012): every rank owns at least one plane of
   // each split - max(p/Nz, p/Ny, 1) <= p1 <= min(Nx, Ny, p)
-  if (p1 > Nx || p1 > Ny || p2 > Ny || p2 > Nz) {
+  if (p1 > Nx || p1 > Ny || p2 > Ny || p2 > (is_r2c ? Nz / 2 + 1 : Nz)) {
     set_error("grid %dx%dx%d cannot be split over %dx%d ranks (P1 outside the reference's range)", Nx, Ny, Nz, p1, p2);
     return -4;
   }
@@ -180,6 +187,7 @@ struct Launch {
   unsigned signal_value = 0;
   unsigned *done_counter = nullptr;
   int grid_cap = 0;
+  int r2c = 0;   // z pass of a real-to-complex plan
   int pdl = 0;   // bit 0: let the next launch of the stream start early; bit 1: this launch may itself start early
 };
 
@@ -237,7 +245,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   if (L.nbatch <= 0 && L.signal_count == 0) return 0;
   if (L.nbatch < 0) L.nbatch = 0;
   FftKernelInfo info;
-  const bool generic = g_force_generic > 0 || L.nbatch == 0 || L.im.gg > 0 || L.om.gg > 0 || !fft_kernel_info(L.N, E.prec, &info);
+  const bool generic = g_force_generic > 0 || L.nbatch == 0 || L.r2c || L.im.gg > 0 || L.om.gg > 0 || !fft_kernel_info(L.N, E.prec, &info);
   if (L.nbatch >= (1LL << 32)) { set_error("batch of %lld rows exceeds the 32-bit batch index", L.nbatch); return -1; }
   FftArgs a;
   memset(&a, 0, sizeof(a));
@@ -257,6 +265,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   a.signal_count = L.signal_count; a.signal_value = L.signal_value; a.done_counter = L.done_counter;
   a.grid_cap = L.grid_cap;
   a.wait_timeout_ns = E.wait_timeout_ns; a.error_word = E.d_error;
+  a.real_mode = L.r2c ? (inverse ? 2 : 1) : 0;
   if (generic) {
     // any length, uneven splits (fft_generic.cu)
     if (!a.tw) { set_error("length %d with this split needs the generic kernel, which holds at most %zu points", L.N, fft_generic_max_n(E.prec)); return -1; }
@@ -294,6 +303,8 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
 }
 
 struct Dims {
+  long long Nzc;   // complex points per z row: Nz, or Nz/2+1 in real-to-complex plans
+  int r2c;
   long long Nx, Ny, Nz, p1, p2, M1, M2, M3, M4, m1, m2, m3, m4, isx, isy, dX, dY, os0, os1, os2;
   int T1, T2, W1, W2, Ry, S;
 };
@@ -302,6 +313,8 @@ Dims dims_of(const struct _offt_plan *po) {
   const struct _offt_comm *c = po->comm;
   Dims d;
   d.Nx = po->Nx; d.Ny = po->Ny; d.Nz = po->Nz; d.p1 = c->p1; d.p2 = c->p2;
+  d.r2c = po->is_r2c ? 1 : 0;
+  d.Nzc = d.r2c ? d.Nz / 2 + 1 : d.Nz;
   d.M1 = c->M1; d.M2 = c->M2; d.M3 = c->M3; d.M4 = c->M4;
   d.m1 = c->m1; d.m2 = c->m2; d.m3 = c->m3; d.m4 = c->m4;
   d.isx = c->istride[0]; d.isy = c->istride[1];
@@ -322,6 +335,7 @@ Launch L_fftz_local(const Dims &d, const void *in, void *out, long long x0, long
   L.N = (int)d.Nz; L.axis = 2; L.in = in; L.out = out;
   L.im = L.om = mk_map(x0 * d.isx, 0, 0, 1, d.m2, d.isy, nx, d.isx, 0);
   L.nbatch = d.m2 * nx; L.load_cfast = L.store_cfast = false;
+  L.r2c = d.r2c;   // real rows of Nz points in, Nz/2+1 complex points out (offt-compute.c:960-961, 3973-3974)
   return L;
 }
 
@@ -329,7 +343,7 @@ Launch L_fftz_local(const Dims &d, const void *in, void *out, long long x0, long
 Launch L_k1(const Dims &d, const void *U, void *send, long long x0, long long myT) {
   Launch L = L_fftz_local(d, U, send, x0, myT);
   // z splits into (destination, z_local): block a at a*myT*M2*M3, inside it [x][y][z_local]
-  L.om = split_over(mk_map(0, d.M3, myT * d.M2 * d.M3, 1, d.m2, d.M3, myT, d.M2 * d.M3, 0), d.Nz, d.p2);
+  L.om = split_over(mk_map(0, d.M3, myT * d.M2 * d.M3, 1, d.m2, d.M3, myT, d.M2 * d.M3, 0), d.Nzc, d.p2);
   return L;
 }
 
@@ -408,23 +422,23 @@ Launch L_fftx_local(const Dims &d, const void *A, void *U) {
 // row stride and stores into the caller's x-y-z layout, and the y pass finishes in place at the row stride.
 Launch L_fftz_swap(const Dims &d, const void *U, void *A) {
   Launch L = L_fftz_local(d, U, A, 0, d.m1);
-  L.om = mk_map(0, 0, 0, 1, d.m2, d.Nx * d.Nz, d.m1, d.Nz, 0);          // A is [y][x][z]
+  L.om = mk_map(0, 0, 0, 1, d.m2, d.Nx * d.M3, d.m1, d.M3, 0);          // A is [y][x][z]
   return L;
 }
 Launch L_fftx_swap(const Dims &d, const void *A, void *U) {
   Launch L;
   L.N = (int)d.Nx; L.axis = 0; L.in = A; L.out = U;
-  L.im = mk_map(0, 0, 0, d.Nz, d.Nz, 1, d.Ny, d.Nx * d.Nz, 0);          // rows along x at the row stride
-  L.om = mk_map(0, 0, 0, d.os0, d.Nz, d.os2, d.Ny, d.os1, 0);
-  L.nbatch = d.Nz * d.Ny; L.load_cfast = L.store_cfast = true;
+  L.im = mk_map(0, 0, 0, d.M3, d.m3, 1, d.Ny, d.Nx * d.M3, 0);          // rows along x at the row stride
+  L.om = mk_map(0, 0, 0, d.os0, d.m3, d.os2, d.Ny, d.os1, 0);
+  L.nbatch = d.m3 * d.Ny; L.load_cfast = L.store_cfast = true;
   return L;
 }
 // y pass in the caller's x-y-z array
 Launch L_ffty_out(const Dims &d, void *U) {
   Launch L;
   L.N = (int)d.Ny; L.axis = 1; L.in = U; L.out = U;
-  L.im = L.om = mk_map(0, 0, 0, d.os1, d.Nz, d.os2, d.Nx, d.os0, 0);
-  L.nbatch = d.Nz * d.Nx; L.load_cfast = L.store_cfast = true;
+  L.im = L.om = mk_map(0, 0, 0, d.os1, d.m3, d.os2, d.Nx, d.os0, 0);
+  L.nbatch = d.m3 * d.Nx; L.load_cfast = L.store_cfast = true;
   return L;
 }
 
@@ -812,8 +826,7 @@ int engine_create(struct _offt_plan *po) {
   World &w = world();
   if (!w.up) { set_error("no world: call offtb_world_init / offtb_world_init_local (or the compat MPI_Init) first"); return -1; }
   const int *v = po->params->v;
-  if (check_supported(po->Nx, po->Ny, po->Nz, po->p, v[_P1_])) return -1;
-  if (po->is_r2c) { set_error("real-to-complex plans are not implemented (complex-to-complex only)"); return -1; }
+  if (check_supported(po->Nx, po->Ny, po->Nz, po->p, v[_P1_], po->is_r2c)) return -1;
   if (v[_T1_] < 1 || v[_T2_] < 1 || v[_W1_] < 0 || v[_W2_] < 0 || v[_W1_] > 64 || v[_W2_] > 64) {
     set_error("tile sizes must be >= 1 and windows in 0..64 (T1 %d W1 %d T2 %d W2 %d)", v[_T1_], v[_W1_], v[_T2_], v[_W2_]);
     return -1;
@@ -830,7 +843,7 @@ int engine_create(struct _offt_plan *po) {
   else if (po->is_oned && c->p1 == 1) E->sched = SCHED_SLAB_1XP;
   else if (po->is_oned && c->p1 == po->p) E->sched = SCHED_SLAB_PX1;
   else E->sched = SCHED_PENCIL;
-  E->alloc = alloc_elems(po->Nx, po->Ny, po->Nz, po->p, c->p1);
+  E->alloc = alloc_elems(po->Nx, po->Ny, po->Nz, po->p, c->p1, po->is_r2c);
   const int Ns[3] = {po->Nx, po->Ny, po->Nz};
   for (int a = 0; a < 3; ++a)
     if (make_twiddles(Ns[a], E->prec, &E->tw[a]) || make_twiddles_full(Ns[a], E->prec, &E->tw_full[a])) return -1;

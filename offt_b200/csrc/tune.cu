@@ -63,7 +63,7 @@ extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int ma
   if (!po || !po->b200) { set_error("null plan"); return -1; }
   if (world().local && world().size > 1) { set_error("tuning runs one rank per process"); return -1; }
   (void)in;
-  const int Nx = po->Nx, Ny = po->Ny, Nz = po->Nz, p = po->p;
+  const int Nx = po->Nx, Ny = po->Ny, Nz = po->is_r2c ? po->Nz / 2 + 1 : po->Nz, p = po->p;   // offt-tuning.c:110, 161
   const auto grid = params_grid(Nx, Ny, Nz, p);
   std::vector<int> best(po->params->v, po->params->v + PARAM_COUNT);
   params_adjust(Nx, Ny, Nz, p, po->is_oned, best.data());

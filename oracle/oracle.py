@@ -121,7 +121,50 @@ def have_reference() -> bool:
     return (REF_DIR / "ref_dump").exists()
 
 
-def run_reference(Nx, Ny, Nz, p, seed, is_oned=0, is_equalxy=0, reps=1, params=None, keep_data=True):
+def scatter_input_r2c(box: RankBox, real_grid: np.ndarray) -> np.ndarray:
+    """in-place r2c input of one rank as a complex128 view of its double array: real (x, y, z) of the box sits at
+    double index z + 2*(istride1*y + istride0*x) (run-fft.c:53-55)"""
+    a = np.zeros(2 * box.alloc, dtype=np.float64)
+    sx, sy, sz = box.isize
+    ix = np.arange(sx)[:, None, None] * (2 * box.istride[0])
+    iy = np.arange(sy)[None, :, None] * (2 * box.istride[1])
+    iz = np.arange(sz)[None, None, :]
+    sub = real_grid[box.istart[0]:box.istart[0] + sx, box.istart[1]:box.istart[1] + sy, box.istart[2]:box.istart[2] + sz]
+    a[(ix + iy + iz).ravel()] = sub.ravel()
+    return a.view(np.complex128)
+
+
+def gather_input_r2c(boxes: list, arrays: list) -> np.ndarray:
+    """global real grid re-assembled from every rank's r2c-layout array (what the backward transform returns)"""
+    Nx, Ny, Nz = boxes[0].N
+    out = np.full((Nx, Ny, Nz), np.nan)
+    for b, a in zip(boxes, arrays):
+        d = np.ascontiguousarray(a).view(np.float64)
+        sx, sy, sz = b.isize
+        ix = np.arange(sx)[:, None, None] * (2 * b.istride[0])
+        iy = np.arange(sy)[None, :, None] * (2 * b.istride[1])
+        iz = np.arange(sz)[None, None, :]
+        out[b.istart[0]:b.istart[0] + sx, b.istart[1]:b.istart[1] + sy, b.istart[2]:b.istart[2] + sz] = d[(ix + iy + iz).ravel()].reshape(sx, sy, sz)
+    return out
+
+
+def gather_output_r2c(boxes: list, dtype=np.complex128) -> np.ndarray:
+    """global [Nx, Ny, Nz/2+1] half spectrum through ostart/osize/ostride"""
+    Nx, Ny, Nz = boxes[0].N
+    out = np.full((Nx, Ny, Nz // 2 + 1), np.nan + 0j, dtype=dtype)
+    for b in boxes:
+        sx, sy, sz = b.osize
+        if sx * sy * sz == 0:
+            continue
+        ix = np.arange(sx)[:, None, None] * b.ostride[0]
+        iy = np.arange(sy)[None, :, None] * b.ostride[1]
+        iz = np.arange(sz)[None, None, :] * b.ostride[2]
+        out[b.ostart[0]:b.ostart[0] + sx, b.ostart[1]:b.ostart[1] + sy, b.ostart[2]:b.ostart[2] + sz] = \
+            b.data[(ix + iy + iz).ravel()].reshape(sx, sy, sz)
+    return out
+
+
+def run_reference(Nx, Ny, Nz, p, seed, is_oned=0, is_equalxy=0, reps=1, params=None, keep_data=True, is_r2c=0):
     """Run the unmodified reference on `p` forked host ranks; returns (boxes, t_min seconds)."""
     params = dict(params or {})
     if P1 not in params:
@@ -131,6 +174,8 @@ def run_reference(Nx, Ny, Nz, p, seed, is_oned=0, is_equalxy=0, reps=1, params=N
         cmd = [str(REF_DIR / "ref_dump"), str(Nx), str(Ny), str(Nz), str(seed), prefix,
                str(int(is_oned)), str(int(is_equalxy)), str(int(reps))]
         cmd += [f"{k}={v}" for k, v in sorted(params.items())]
+        if is_r2c:
+            cmd.append("r2c=1")
         env = dict(os.environ, OFFT_SHIM_NP=str(p))
         res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3600)
         if res.returncode != 0:

@@ -8,8 +8,9 @@
  * rank's descriptor and raw in-place output array to <prefix>.rank<r>.bin.
  * Used to pin oracle/offt_oracle.c and to generate tests/golden/.
  *
- * usage: OFFT_SHIM_NP=P ref_dump Nx Ny Nz seed prefix is_oned is_equalxy reps [idx=value ...]
- *        (idx=value overrides custom_params->v[idx], e.g. 0=4 sets _P1_ to 4)
+ * usage: OFFT_SHIM_NP=P ref_dump Nx Ny Nz seed prefix is_oned is_equalxy reps [idx=value ...] [r2c=1]
+ *        (idx=value overrides custom_params->v[idx], e.g. 0=4 sets _P1_ to 4; r2c=1 runs the real-to-complex
+ *        transform of the grid's real parts, input laid out as run-fft.c:53-55 does)
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -39,18 +40,20 @@ int main(int argc, char **argv) {
   int is_oned = atoi(argv[6]), is_equalxy = atoi(argv[7]), reps = atoi(argv[8]);
   struct _offt_params *cp = (struct _offt_params *)malloc(sizeof(*cp));
   for (i = 0; i < PARAM_COUNT; i++) cp->v[i] = -1;
+  int is_r2c = 0;
   for (i = 9; i < argc; i++) {
     int idx, val;
+    if (sscanf(argv[i], "r2c=%d", &val) == 1) { is_r2c = val; continue; }
     if (sscanf(argv[i], "%d=%d", &idx, &val) == 2 && idx >= 0 && idx < PARAM_COUNT) cp->v[idx] = val;
   }
   int p1 = cp->v[_P1_];
   if (p1 < 0) { fprintf(stderr, "ref_dump: P1 (0=value) is required\n"); return 2; }
   int p2 = p / p1;
   /* allocation rule of run-fft.c:294-304, in 64-bit */
-  long M1 = (Nx + p1 - 1) / p1, M2 = (Ny + p2 - 1) / p2, M3 = (Nz + p2 - 1) / p2, M4 = (Ny + p1 - 1) / p1;
+  long M1 = (Nx + p1 - 1) / p1, M2 = (Ny + p2 - 1) / p2, M3 = ((is_r2c ? Nz / 2 + 1 : Nz) + p2 - 1) / p2, M4 = (Ny + p1 - 1) / p1;
   long size = (M2 * p2 > M4 * p1) ? M1 * M2 * M3 * p2 : M1 * M3 * M4 * p1;
   double *out = (double *)calloc((size_t)size * 2, sizeof(double));
-  struct _offt_plan *po = offt_3d_init(Nx, Ny, Nz, out, out, 0, FFTW_ESTIMATE, is_oned, 0, is_equalxy,
+  struct _offt_plan *po = offt_3d_init(Nx, Ny, Nz, out, out, is_r2c, FFTW_ESTIMATE, is_oned, 0, is_equalxy,
                                         1, 0, 0, 0, 0, 0, cp);
   struct _offt_comm *c = po->comm;
   double tmin = 1e30;
@@ -64,6 +67,10 @@ int main(int argc, char **argv) {
           uint64_t g = ((uint64_t)(x + c->istart[0]) * (uint64_t)Ny + (uint64_t)(y + c->istart[1])) * (uint64_t)Nz
                        + (uint64_t)(z + c->istart[2]);
           size_t a = (size_t)z * c->istride[2] + (size_t)y * c->istride[1] + (size_t)x * c->istride[0];
+          if (is_r2c) {   /* run-fft.c:53-55: real z of row (x, y) at double index z + 2*(row start) */
+            out[(size_t)z + 2 * ((size_t)y * c->istride[1] + (size_t)x * c->istride[0])] = grid_value(seed, 2 * g);
+            continue;
+          }
           out[2 * a] = grid_value(seed, 2 * g);
           out[2 * a + 1] = grid_value(seed, 2 * g + 1);
         }

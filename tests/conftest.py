@@ -18,11 +18,11 @@ def oracle():
     return O.Oracle()
 
 
-def load_golden(name):
+def load_golden(name, sub=""):
     """fixture written by tests/golden/make_golden.py from the unmodified reference"""
     import numpy as np
     from oracle import oracle as O
-    z = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+    z = np.load(ROOT / "tests" / "golden" / sub / f"{name}.npz")
     N = tuple(int(v) for v in z["N"])
     p = int(z["p"])
     boxes, off = [], 0
@@ -39,5 +39,5 @@ def load_golden(name):
                 custom=custom, params=[int(v) for v in z["params"]], boxes=boxes)
 
 
-def golden_names():
-    return sorted(f.stem for f in (ROOT / "tests" / "golden").glob("*.npz"))
+def golden_names(sub=""):
+    return sorted(f.stem for f in (ROOT / "tests" / "golden" / sub).glob("*.npz"))

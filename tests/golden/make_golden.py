@@ -39,6 +39,15 @@ CASES = {
     "uneven_6ranks": ((20, 12, 18), 6, 0, 0, {P1: 3, V: 3, T1: 3, T2: 4}),
 }
 SEED = 20161
+# real-to-complex plans (is_r2c = 1): the real parts of the same seeded grid, fixtures in tests/golden/r2c/
+R2C_CASES = {
+    "r2c_single_12_10_9": ((12, 10, 9), 1, 0, 0, {P1: 1}),
+    "r2c_single_stride_16_8_32": ((16, 8, 32), 1, 1, 0, {P1: 1, S: 1}),
+    "r2c_slab_px1_16_8_32": ((16, 8, 32), 4, 1, 0, {P1: 4}),
+    "r2c_slab_1xp_stride_16_8_32": ((16, 8, 32), 4, 1, 0, {P1: 1, S: 1}),
+    "r2c_pencil_2x2_12_10_18_a2av": ((12, 10, 18), 4, 0, 0, {P1: 2, V: 3}),
+    "r2c_pencil_2x4_32_64_16": ((32, 64, 16), 8, 0, 0, {P1: 2, T1: 4, T2: 2}),
+}
 
 if __name__ == "__main__":
     if not O.have_reference():
@@ -56,3 +65,16 @@ if __name__ == "__main__":
             data=np.concatenate([b.data for b in boxes]))
         err = O.rel_l2(O.gather_output(boxes), np.fft.fftn(O.grid_values(SEED, *N)))
         print(f"{name}: p={p} N={N} rel-L2 vs numpy {err:.2e}")
+    (out_dir / "r2c").mkdir(exist_ok=True)
+    for name, (N, p, oned, eq, params) in R2C_CASES.items():
+        boxes, _ = O.run_reference(*N, p, seed=SEED, is_oned=oned, is_equalxy=eq, params=params, is_r2c=1)
+        desc = np.array([[b.p1, b.p2, *b.istart, *b.isize, *b.istride, *b.ostart, *b.osize, *b.ostride, b.alloc]
+                         for b in boxes], dtype=np.int64)
+        np.savez_compressed(
+            out_dir / "r2c" / f"{name}.npz",
+            N=np.array(N), p=p, is_oned=oned, is_equalxy=eq, seed=SEED, is_r2c=1,
+            custom=np.array(sorted(params.items()), dtype=np.int64).reshape(-1, 2),
+            params=np.array(boxes[0].params, dtype=np.int32), desc=desc,
+            data=np.concatenate([b.data for b in boxes]))
+        err = O.rel_l2(O.gather_output_r2c(boxes), np.fft.rfftn(O.grid_values(SEED, *N).real))
+        print(f"{name}: p={p} N={N} r2c rel-L2 vs numpy rfftn {err:.2e}")

@@ -24,7 +24,7 @@ def box_of(plan, N, p):
                      alloc=plan.alloc_elems, params=plan.params)
 
 
-def gpu_forward(grid, p, custom, is_oned=0, is_equalxy=0, bits=64, host_arrays=False, inverse_too=False):
+def gpu_forward(grid, p, custom, is_oned=0, is_equalxy=0, bits=64, host_arrays=False, inverse_too=False, is_r2c=0):
     """forward 3-D FFT of the global `grid` on p emulated ranks of one GPU through the C API.
     Returns (boxes with .data = each rank's in-place array after the transform, plans' launch count,
     optionally the arrays after a following backward transform)."""
@@ -35,9 +35,14 @@ def gpu_forward(grid, p, custom, is_oned=0, is_equalxy=0, bits=64, host_arrays=F
     with local_world(p) as ob:
         ob.set_default_precision(bits)
         try:
-            plans = [ob.Plan(*N, is_oned=is_oned, is_equalxy=is_equalxy, is_notest=1, custom=custom, rank=r) for r in range(p)]
+            plans = [ob.Plan(*N, is_oned=is_oned, is_equalxy=is_equalxy, is_notest=1, custom=custom, rank=r, is_r2c=is_r2c) for r in range(p)]
             boxes = [box_of(pl, N, p) for pl in plans]
-            host = [np.ascontiguousarray(O.scatter_input(b, grid.astype(cdt))) for b in boxes]
+            if is_r2c:   # real input in the in-place r2c layout (run-fft.c:53-55), handed over as the complex view of the doubles
+                host = [np.ascontiguousarray(O.scatter_input_r2c(b, np.asarray(grid.real, dtype=np.float64))) for b in boxes]
+                if bits == 32:
+                    host = [h.view(np.float64).astype(np.float32).view(np.complex64) for h in host]
+            else:
+                host = [np.ascontiguousarray(O.scatter_input(b, grid.astype(cdt))) for b in boxes]
             if host_arrays:
                 arrays = host
             else:

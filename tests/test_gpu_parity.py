@@ -350,3 +350,36 @@ def test_single_rank_xyz_schedule(oracle, N, bits):
     A = O.gather_output(got, cdt)
     assert O.rel_l2(A, want) < TOL[bits] and O.rel_l2(A, np.fft.fftn(grid)) < TOL[bits]
     assert O.rel_l2(gather_input(got, back, cdt) / np.prod(N), grid) < TOL[bits]
+
+
+# ---------------------------------------------------------------- real-to-complex plans (is_r2c, offt-compute.c:63, 334-336, 960-961)
+@pytest.mark.parametrize("name", golden_names("r2c"))
+def test_r2c_plan_matches_reference_fixture(name):
+    """fixtures = outputs of the unmodified reference run with is_r2c = 1 (tests/golden/make_golden.py)"""
+    _torch()
+    g = load_golden(name, "r2c")
+    grid = O.grid_values(g["seed"], *g["N"])
+    got, _, _ = gpu_forward(grid, g["p"], g["custom"], g["is_oned"], g["is_equalxy"], is_r2c=1)
+    assert got[0].params == g["params"]
+    for a, b in zip(got, g["boxes"]):
+        assert (a.istart, a.isize, a.istride, a.ostart, a.osize, a.ostride, a.alloc) == \
+               (b.istart, b.isize, b.istride, b.ostart, b.osize, b.ostride, b.alloc)
+    assert O.rel_l2(O.gather_output_r2c(got), O.gather_output_r2c(g["boxes"])) < 1e-12
+
+
+@pytest.mark.parametrize("N,p,oned,custom,bits", [
+    ((64, 32, 128), 1, 0, {P.P1: 1}, 64), ((64, 32, 128), 1, 0, {P.P1: 1, P.S: 1}, 64), ((32, 64, 256), 4, 1, {P.P1: 4}, 64),
+    ((32, 64, 250), 4, 1, {P.P1: 1, P.S: 1, P.T1: 5}, 64), ((30, 24, 50), 6, 0, {P.P1: 3, P.V: 3}, 64), ((64, 64, 64), 8, 0, {P.P1: 2, P.T1: 8, P.T2: 5}, 64),
+    ((64, 32, 128), 4, 0, {P.P1: 2}, 32)])
+def test_r2c_matches_numpy_and_round_trips(N, p, oned, custom, bits):
+    """half spectrum against numpy.fft.rfftn; the backward transform (complex-to-real) returns N * the real input"""
+    _torch()
+    grid = O.grid_values(12, *N)
+    want = np.fft.rfftn(grid.real)
+    got, launches, back = gpu_forward(grid, p, custom, oned, 0, bits=bits, inverse_too=True, is_r2c=1)
+    assert launches > 0
+    cdt = np.complex128 if bits == 64 else np.complex64
+    assert O.rel_l2(O.gather_output_r2c(got, cdt), want) < TOL[bits]
+    if bits == 32:
+        back = [b.view(np.float32).astype(np.float64).view(np.complex128) for b in back]
+    assert O.rel_l2(O.gather_input_r2c(got, back) / np.prod(N), grid.real) < TOL[bits]
