@@ -435,6 +435,7 @@ def measure_config(cx, N, *, bits, oned, custom, steps, tune=0, label=""):
     ob.set_default_precision(bits)
     try:
         plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom=custom)
+        plan.set_stage_timing(False)
         alloc = plan.alloc_elems
         rdt = torch.float64 if bits == 64 else torch.float32
         g = torch.Generator(device=cx.dev); g.manual_seed(99 + cx.rank)
@@ -442,11 +443,20 @@ def measure_config(cx, N, *, bits, oned, custom, steps, tune=0, label=""):
         w = torch.empty_like(x0)
         out = {"workload": label, "grid": list(N), "bits": bits}
         if tune > 0:
-            w.copy_(x0)
+            # the default point first, then the library's search over T, W, Ry, S and the decomposition P1 (every trial
+            # rebuilds the layout, offt-tuning.c:929-948, and runs on an internal zeroed array), then the arrays again
             out["default_params"] = {ob.PARAM_NAMES[i]: plan.params[i] for i in (P.P1, P.T1, P.W1, P.T2, P.W2, P.Ry, P.S)}
-            w.copy_(x0); cx.barrier(); plan.execute(w); w.copy_(x0); cx.barrier(); plan.execute(w)
+            for _ in range(3):
+                w.copy_(x0); cx.barrier(); plan.execute(w)
             out["default_ms"] = round(cx.max_over_ranks([plan.last_ms])[0], 4)
-            out["tune_trials"] = plan.tune(w, tune, verbose=0)
+            del x0, w
+            torch.cuda.empty_cache()
+            out["tune_trials"] = plan.tune_ex(tune, strategy=3, search_p1=True)
+            plan.set_stage_timing(False)
+            alloc = plan.alloc_elems
+            g = torch.Generator(device=cx.dev); g.manual_seed(99 + cx.rank)
+            x0 = torch.view_as_complex(torch.rand((alloc, 2), generator=g, device=cx.dev, dtype=rdt) * 2 - 1)
+            w = torch.empty_like(x0)
         times = []
         for i in range(steps + 2):
             w.copy_(x0); cx.barrier()
@@ -535,6 +545,7 @@ def own_arm(args):
         plan.execute(work)            # synchronous; device time first->last kernel in plan.last_ms
         return plan.last_ms, plan.last_launches
 
+    plan.set_stage_timing(False)  # the timed steps carry no per-launch events; the per-kernel pass below turns them on
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()            # nvidia-smi needs a few hundred ms to come up: start it before the warm-up
@@ -657,8 +668,8 @@ def own_arm(args):
         if world == 8 and N == (1024, 1024, 1024):
             extra_configs.append(measure_config(cx, (2048, 2048, 2048), bits=64, oned=0, custom={P.P1: 2, P.S: 0}, steps=3,
                                                 label="configs[3]: 2048^3 complex128 forward, pencil 2x4, 8 GPUs"))
-            extra_configs.append(measure_config(cx, (2048, 1024, 512), bits=32, oned=1, custom={P.P1: 8, P.S: 0}, steps=5, tune=16,
-                                                label="configs[4]: 2048x1024x512 complex64 forward, 8 GPUs, tunables searched (offtb_tune)"))
+            extra_configs.append(measure_config(cx, (2048, 1024, 512), bits=32, oned=1, custom={P.P1: 8, P.S: 0}, steps=5, tune=24,
+                                                label="configs[4]: 2048x1024x512 complex64 forward, 8 GPUs, tile / window / P1 searched (offtb_tune_ex, coordinate descent incl. the decomposition)"))
 
     ob.world_fin()
     if world > 1:

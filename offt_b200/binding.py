@@ -100,6 +100,7 @@ def _load():
     L.offtb_alloc_elems_r2c.argtypes = [i] * 6
     L.offtb_check_supported.argtypes = [i] * 5
     L.offtb_tune.argtypes = [C.POINTER(OfftPlan), vp, vp, i, i]
+    L.offtb_tune_ex.argtypes = [C.POINTER(OfftPlan), vp, vp, i, i, i, i]
     L.offtb_set_exit_on_error(0)   # Python raises instead of exit(-1)
     return L
 
@@ -237,6 +238,14 @@ class Plan:
         n = lib.offtb_tune(self.po, ptr, ptr, max_loop, verbose)
         if n < 0:
             raise OfftError(f"offtb_tune: {_err()}")
+        return n
+
+    def tune_ex(self, max_loop=20, strategy=3, search_p1=False, verbose=0) -> int:
+        """the search of tune.cu: strategy 0/1 Nelder-Mead from the reference's initial simplex, 2 random, 3 coordinate
+        descent; search_p1 also moves the decomposition (read .comm / .alloc_elems again afterwards)"""
+        n = lib.offtb_tune_ex(self.po, None, None, max_loop, verbose, strategy, int(search_p1))
+        if n < 0:
+            raise OfftError(f"offtb_tune_ex: {_err()}")
         return n
 
     @property

@@ -20,8 +20,14 @@ static double now_s() {
 
 static Engine *eng(const struct _offt_plan *po) { return po ? (Engine *)po->b200 : nullptr; }
 
-// po->t[]: the reference's 16 wall-clock buckets (offt.h:171-188) filled from device time.
-// The fused kernels are booked under the FFT they contain; pack/unpack have no time of their own.
+// po->t[]: the reference's 16 wall-clock buckets (offt.h:171-188), filled on every execute from CUDA events.
+//   ALL                      first kernel -> last kernel (host <-> device copies included when the caller passed host memory)
+//   FFTz, FFTy1, FFTy2, FFTx the four fused launches K1..K4 (a dependent-launch chain is booked as its span)
+//   WAIT1, WAIT2             device time of the exchanges where they are separate operations (NCCL send/recv mode);
+//                            in the fused exchange the NVLink stores are part of FFTz / FFTy2
+//   INIT1, INIT2             host seconds spent enqueueing the phase - what posting the collectives costs the caller
+//   PACK*, UNPACK*, TRANSPOSE always 0: those steps are the address maps of the FFT launches, they have no time of their own
+//   TEST1, TEST2             always 0: there is no MPI_Test to poll
 static void fill_timers(struct _offt_plan *po) {
   Engine *E = eng(po);
   double *t = po->t;
@@ -33,8 +39,10 @@ static void fill_timers(struct _offt_plan *po) {
   t[FFTy1] = s[ST_K2] * 1e-3;
   t[FFTy2] = s[ST_K3] * 1e-3;
   t[FFTx] = s[ST_K4] * 1e-3;
-  t[WAIT1] = s[ST_X1] * 1e-3;   // device time of the exchanges (overlapped with compute when W > 0)
+  t[WAIT1] = s[ST_X1] * 1e-3;
   t[WAIT2] = s[ST_X2] * 1e-3;
+  t[INIT1] = E->post_s[0];
+  t[INIT2] = E->post_s[1];
 }
 }  // namespace offtb
 
@@ -90,7 +98,9 @@ struct _offt_plan *offt_3d_init(int Nx, int Ny, int Nz, double *in, double *out,
   params_default(Nx, Ny, is_r2c ? Nz / 2 + 1 : Nz, po->p, is_W0, is_notest, po->params->v);
   po->params->is_converged = 1;
   if (!po->rank) print_params(po->params->v);
-  if (custom_params)
+  // the caller's overrides count only without tuning: the reference's tuner starts from the defaults and searches all
+  // 24 tunables itself ("custom values must be adjusted for tuning", offt-compute.c:3417-3423)
+  if (custom_params && max_loop == 0)
     for (int i = 0; i < PARAM_COUNT; ++i)
       if (custom_params->v[i] >= 0) po->params->v[i] = custom_params->v[i];
   int rc = 0;
@@ -308,13 +318,13 @@ double offtb_fft_rows(void *data, int n, long long stride, long long dist, long 
 }
 
 // ---- tuning --------------------------------------------------------------------------------------
-// The shape of the reference's loop (ah_tuning, offt-tuning.c:879-1006): fetch a candidate point,
-// repair it (ADJUST_POINT), test feasibility, skip points already measured, measure one execute,
-// report; finally install the best point.  The candidate source is a built-in coordinate search over
-// the knobs that matter on a GPU (T1, W1, T2, W2) on the reference's value grid instead of the Active
-// Harmony server (DESIGN.md sections 1 and 5).
-int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose);
+// ah_tuning (offt-tuning.c:744-1022) as offt_3d_init calls it (offt-compute.c:3440): the search of tune.cu with the
+// strategy the caller chose (-s: 0 Nelder-Mead, 1 PRO -> Nelder-Mead, 2 random, 3 brute -> coordinate descent), over
+// all decompositions (the caller lays out its array only after init returns, run-fft.c:269-304, 314)
+int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1);
 
-int ah_tuning(struct _offt_plan *po, double *in, double *out) { return offtb_tune(po, in, out, po->max_loop, !po->rank); }
+int ah_tuning(struct _offt_plan *po, double *in, double *out) {
+  return offtb_tune_ex(po, in, out, po->max_loop, !po->rank, po->ah_strategy, 1);
+}
 
 }  // extern "C"

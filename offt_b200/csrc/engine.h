@@ -63,6 +63,8 @@ void params_default(int Nx, int Ny, int Nz, int p, int is_W0, int is_notest, int
 int params_infeasible(int Nx, int Ny, int Nz, int p, const int *v, int *bad);
 void params_adjust(int Nx, int Ny, int Nz, int p, int is_oned, int *v);
 const char *param_name(int i);
+void initial_simplex(int Nx, int Ny, int Nz, int p, int is_oned, int is_W0, int is_notest, int tuning_mode,
+                     int **v_list, int *v_list_size, int (*x)[PARAM_COUNT]);
 
 // ---- layout (plan.cu) ---------------------------------------------------------------------
 void comm_fill(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int p1, int rank, int S, int is_equalxy, int is_r2c = 0);
@@ -122,7 +124,8 @@ struct Engine {
   Ring ring[2];
   cudaStream_t s_comp = nullptr, s_comm = nullptr, s_user = nullptr;
   bool async = false;
-  bool stage_timing = false;
+  bool stage_timing = true;      // CUDA events around every launch (or chain of launches) feed the reference's po->t[] buckets
+  double post_s[2] = {0.0, 0.0}; // host seconds spent enqueueing phase 1 / phase 2 (the INIT1 / INIT2 "posting cost" buckets)
   void *registered_host = nullptr;
   size_t registered_bytes = 0;
   int launches = 0;

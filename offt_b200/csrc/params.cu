@@ -200,6 +200,104 @@ void params_adjust(int Nx, int Ny, int Nz, int p, int is_oned, int *v) {
   if (Nx % p1 == 0 && Ny % p1 == 0) v[_V_] &= 2;
 }
 
+// The starting simplex of the reference's tuner (write_initial_simplex, offt-tuning.c:426-737), re-derived as a table of
+// windows: every tunable of every vertex is drawn uniformly - one rand() per tunable, in index order, exactly as the
+// reference consumes them, so the same srand() seed gives the same vertices - from the grid points inside a window
+// [lo, hi] that depends on the tunables drawn before it:
+//   P1        its whole grid (tuning_mode 1 / 2 pin it to 1 / p); vertices 0-1, 2-3, 4-5, 6-7 take the smallest, largest,
+//             lower-middle and upper-middle grid point instead of the random one (:662-678)
+//   T1, T2    between "at least 64 elements per message" and "at most BUFFER_SIZE_LIMIT/8 elements per buffer"
+//   W1, W2    0..5, capped by the tile count and by the buffer budget; 0 for a single tile or is_W0
+//   sub-tiles pairs (first, second) sized around the cache budget SUBTILE_SIZE: first in [sqrt(S/8/L), sqrt(16 S/L)]
+//             stretched by the other extent, second so that first*second*L stays within [S/8, 16 S]
+//   MPI_Test frequencies  between g/8 and 32 g (8 g for Fy2) calls, g = ranks of the phase's group; 0 when is_notest
+//   Ry 0..min(10, M1) (pinned for slabs), V 0..3, S 0..1
+void initial_simplex(int Nx, int Ny, int Nz, int p, int is_oned, int is_W0, int is_notest, int tuning_mode,
+                     int **v_list, int *v_list_size, int (*x)[PARAM_COUNT]) {
+  auto isqrt = [](int n) { return (int)std::sqrt((double)n); };
+  const int S8 = SUBTILE_SIZE / 8, S16 = SUBTILE_SIZE * 16;
+  for (int i = 0; i < PARAM_COUNT + 1; ++i) {
+    int vv[PARAM_COUNT];
+    int p1 = 1, p2 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0;
+    // first member of a sub-tile pair: 1..cap around sqrt of the budget over row length L, stretched by the other extent Mo
+    auto pair_first = [&](int cap, int L, int Mo, int &lo, int &hi) {
+      lo = std::max(1, std::min(std::min(cap, isqrt(S8 / L)), S8 / L / Mo));
+      hi = std::min(cap, std::max(std::max(lo, isqrt(S16 / L)), S16 / L / Mo));
+    };
+    auto pair_second = [&](int cap, int L, int first, int &lo, int &hi) {
+      lo = std::max(1, std::min(cap, S8 / L / first));
+      hi = std::min(cap, std::max(lo, S16 / L / first));
+    };
+    auto freq = [&](int cap, int g, int mult, int &lo, int &hi) {
+      lo = std::max(0, std::min(cap, g / 8));
+      hi = std::min(cap, std::max(lo, g * mult));
+      if (is_notest) lo = hi = 0;
+    };
+    auto window = [&](int planes, int T, int slab, int &lo, int &hi) {   // W of a phase with tile T, slab = elements per plane of the ring
+      lo = hi = 0;
+      if (is_W0 || planes == T) return;
+      hi = std::min(5, std::max(0, std::min((planes + T - 1) / T, BUFFER_SIZE_LIMIT / 2 / 2 / (T * slab) - 1)));
+    };
+    for (int j = 0; j < PARAM_COUNT; ++j) {
+      int lo = 0, hi = 0;
+      switch (j) {
+        case _P1_: lo = tuning_mode == 2 ? p : 1; hi = tuning_mode == 1 ? 1 : p; break;
+        case _T1_:
+          lo = std::max(1, std::min(M1, 64 * p2 / M2 / (M3 * p2)));
+          hi = std::min(M1, std::max(lo, (BUFFER_SIZE_LIMIT / 8) / M2 / (M3 * p2)));
+          break;
+        case _W1_: window(M1, vv[_T1_], M2 * (M3 * p2), lo, hi); break;
+        case _Px1_: pair_first(vv[_T1_], Nz, M2, lo, hi); break;
+        case _Py1_: pair_second(M2, Nz, vv[_Px1_], lo, hi); break;
+        case _Fz_: freq(vv[_T1_] * M2, p2, 32, lo, hi); break;
+        case _FP1_: freq(vv[_T1_] / vv[_Px1_] * M2 / vv[_Py1_], p2, 32, lo, hi); break;
+        case _Ux1_: pair_first(vv[_T1_], Ny, M3, lo, hi); break;
+        case _Uz1_: pair_second(M3, Ny, vv[_Ux1_], lo, hi); break;
+        case _FU1_: freq(vv[_T1_] / vv[_Ux1_] * M3 / vv[_Uz1_], p2, 32, lo, hi); break;
+        case _Fy1_: freq(vv[_T1_] * M3, p2, 32, lo, hi); break;
+        case _Ry_:
+          lo = 0; hi = std::min(10, std::max(0, M1));
+          if (is_oned && p1 == 1) lo = hi;
+          else if (is_oned && p1 == p) lo = hi = 0;
+          break;
+        case _T2_:
+          lo = std::max(1, std::min(M3, 64 * p1 / M1 / (M4 * p1)));
+          hi = std::min(M3, std::max(lo, (BUFFER_SIZE_LIMIT / 8) / M1 / (M4 * p1)));
+          break;
+        case _W2_: window(M3, vv[_T2_], M1 * (M4 * p1), lo, hi); break;
+        case _Fy2_: freq(vv[_T2_] * M1, p1, 8, lo, hi); break;
+        case _Pz2_: pair_first(vv[_T2_], Ny, M1, lo, hi); break;
+        case _Px2_: pair_second(M1, Ny, vv[_Pz2_], lo, hi); break;
+        case _FP2_: freq(vv[_T2_] / vv[_Pz2_] * M1 / vv[_Px2_], p1, 32, lo, hi); break;
+        case _Uz2_: pair_first(vv[_T2_], Nx, M4, lo, hi); break;
+        case _Uy2_: pair_second(M4, Nx, vv[_Uz2_], lo, hi); break;
+        case _FU2_: freq(vv[_T2_] / vv[_Uz2_] * M4 / vv[_Uy2_], p1, 32, lo, hi); break;
+        case _Fx_: freq(vv[_T2_] * M4, p1, 32, lo, hi); break;
+        case _V_: lo = 0; hi = 3; break;
+        case _S_: lo = 0; hi = 1; break;
+      }
+      const int g_hi = grid_value_floor(1, v_list, v_list_size, j, hi);
+      int g_lo = grid_value_ceil(1, v_list, v_list_size, j, lo);
+      if (g_lo > g_hi) g_lo = g_hi;
+      x[i][j] = (rand() % (g_hi - g_lo + 1)) + g_lo;
+      if (j == _P1_) {
+        if (i < 2) x[i][j] = g_lo;
+        else if (i < 4) x[i][j] = g_hi;
+        else if (i < 6) x[i][j] = (g_lo + g_hi) / 2;
+        else if (i < 8) x[i][j] = (g_lo + g_hi + 1) / 2;
+      }
+      vv[j] = v_list[j][x[i][j]];
+      if (j == _P1_) {
+        p1 = vv[_P1_]; p2 = p / p1;
+        M1 = (Nx + p1 - 1) / p1; M2 = (Ny + p2 - 1) / p2; M3 = (Nz + p2 - 1) / p2; M4 = (Ny + p1 - 1) / p1;
+      }
+    }
+    // slabs: the phase that does not run has no y rows to balance (the other repairs are params_convert's, ADJUST_POINT)
+    if (is_oned && p1 == 1) x[i][_Ry_] = 10;
+    if (is_oned && p1 == p) x[i][_Ry_] = 0;
+  }
+}
+
 const char *param_name(int i) { return kSpec[i].name; }
 
 }  // namespace offtb
@@ -208,8 +306,11 @@ using namespace offtb;
 
 extern "C" {
 
+// z extent every tunable is sized by: Nz, or the Nz/2+1 complex points of a real-to-complex plan (offt-compute.c:3008, 3045, 3141)
+static int nz_eff(const struct _offt_plan *po) { return po->is_r2c ? po->Nz / 2 + 1 : po->Nz; }
+
 void params_range_setup(struct _offt_plan *po, int **v_list, int *v_list_size) {
-  const auto g = params_grid(po->Nx, po->Ny, po->Nz, po->p);   // C2C only: Nz_new == Nz
+  const auto g = params_grid(po->Nx, po->Ny, nz_eff(po), po->p);
   for (int i = 0; i < PARAM_COUNT; ++i) {
     v_list_size[i] = (int)g[i].size();
     v_list[i] = (int *)malloc(sizeof(int) * std::max<size_t>(g[i].size(), 1));   // caller frees, as in the reference
@@ -238,7 +339,7 @@ void params_convert(int is_backward, int *v, long *ahv, struct _offt_plan *po, i
       if (ahv[i] < 0 || ahv[i] >= v_list_size[i]) { printf("params_convert: bwd OUT OF RANGE ERROR\n"); exit(-1); }
       v[i] = v_list[i][ahv[i]];
     }
-    params_adjust(po->Nx, po->Ny, po->Nz, po->p, po->is_oned, v);
+    params_adjust(po->Nx, po->Ny, nz_eff(po), po->p, po->is_oned, v);
   } else {
     for (int i = 0; i < PARAM_COUNT; ++i) {
       long found = -1;
@@ -251,12 +352,26 @@ void params_convert(int is_backward, int *v, long *ahv, struct _offt_plan *po, i
 }
 
 // offt-tuning.c:144-226: 1 and the offending tunable in *p_i if the relations among the parameters do not hold
-int is_infeasible_point(struct _offt_plan *po, int *v, int *p_i) { return params_infeasible(po->Nx, po->Ny, po->Nz, po->p, v, p_i); }
+int is_infeasible_point(struct _offt_plan *po, int *v, int *p_i) { return params_infeasible(po->Nx, po->Ny, nz_eff(po), po->p, v, p_i); }
 
 // offt-compute.c:3127-3225: heuristic defaults into po->params->v (computed for P1 = floor(sqrt(p)) on the grid,
 // before any -d override, as in the reference)
 void params_set_default(struct _offt_plan *po) {
-  params_default(po->Nx, po->Ny, po->Nz, po->p, po->is_W0, po->is_notest, po->params->v);
+  params_default(po->Nx, po->Ny, nz_eff(po), po->p, po->is_W0, po->is_notest, po->params->v);
+}
+
+// offt-tuning.c:426-737: the 25 starting vertices of the Nelder-Mead search, in grid-index space, written one per
+// line to po->user_vertex_file (the patched nm.so reads them, strategies/nm.c:369-396)
+void write_initial_simplex(struct _offt_plan *po, int **v_list, int *v_list_size) {
+  int x[PARAM_COUNT + 1][PARAM_COUNT];
+  initial_simplex(po->Nx, po->Ny, nz_eff(po), po->p, po->is_oned, po->is_W0, po->is_notest, po->tuning_mode, v_list, v_list_size, x);
+  FILE *f = fopen(po->user_vertex_file, "w");
+  if (!f) { printf("write_initial_simplex: cannot write %s\n", po->user_vertex_file); exit(-1); }
+  for (int i = 0; i < PARAM_COUNT + 1; ++i) {
+    for (int j = 0; j < PARAM_COUNT; ++j) fprintf(f, "%d ", x[i][j]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
 }
 
 void print_params(int *v) {

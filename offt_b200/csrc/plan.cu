@@ -16,6 +16,7 @@
 // between send and receive slots on a second stream, ordered by cudaEvents, remain as the
 // fallback (OFFTB_EXCHANGE=nccl, or when the peers' rings cannot be mapped).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -275,7 +276,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
       return 0;
     }
     cudaEvent_t g0 = nullptr, g1 = nullptr;
-    const bool gtimed = E.stage_timing && !E.chain_timing;
+    const bool gtimed = E.stage_timing && !E.async && !E.chain_timing;
     if (gtimed) { g0 = pool_event(E); g1 = pool_event(E); cudaEventRecord(g0, st); }
     cudaError_t ge = fft_generic_launch(L.N, E.prec, a, L.nbatch, st, nullptr);
     if (ge != cudaSuccess) { set_error("generic kernel launch (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(ge)); return -1; }
@@ -293,7 +294,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
     return 0;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  const bool timed = E.stage_timing && !E.chain_timing;
+  const bool timed = E.stage_timing && !E.async && !E.chain_timing;
   if (timed) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
   cudaError_t err = fft_launch(L.N, E.prec, a, L.nbatch, st);
   if (err != cudaSuccess) { set_error("kernel launch (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(err)); return -1; }
@@ -475,7 +476,8 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, const std::vector
     char *dst = (char *)(inverse ? R.send[slot] : R.recv[slot]);
     const size_t bytes = (size_t)blk * E.esz;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
+    const bool xtimed = E.stage_timing && !E.async;
+    if (xtimed) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); }
     if (w.local) {
       // every emulated rank pulls its blocks out of its peers' slots
       for (size_t j = 0; j < members.size(); ++j) {
@@ -501,7 +503,7 @@ int exchange(std::vector<Engine *> &engs, int phase, int slot, const std::vector
       OFFTB_NCCL(nc->GroupEnd());
       OFFTB_CUDA(cudaMemcpyAsync(dst + (size_t)me * bytes, src + (size_t)me * bytes, bytes, cudaMemcpyDeviceToDevice, st));
     }
-    if (E.stage_timing) { cudaEventRecord(e1, st); E.timed.push_back({phase == 1 ? ST_X1 : ST_X2, {e0, e1}}); }
+    if (xtimed) { cudaEventRecord(e1, st); E.timed.push_back({phase == 1 ? ST_X1 : ST_X2, {e0, e1}}); }
   }
   return 0;
 }
@@ -713,7 +715,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   const bool pdl = two && pdl_env;
   int n_first = 0, n_second = 0;
   cudaEvent_t ce[4] = {nullptr, nullptr, nullptr, nullptr};
-  E0.chain_timing = pdl && E0.stage_timing;
+  E0.chain_timing = pdl && E0.stage_timing && !E0.async;
   if (E0.chain_timing) for (cudaEvent_t &e : ce) e = pool_event(E0);
   auto first = [&](size_t k, int i) {
     Engine &E = *engs[k];
@@ -793,7 +795,10 @@ int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inve
   if (inverse) std::reverse(steps.begin(), steps.end());
   for (Step s : steps) {
     if (s == STEP_PHASE1 || s == STEP_PHASE2) {
+      const auto h0 = std::chrono::steady_clock::now();
       if (run_phase(engs, bufs, s == STEP_PHASE1 ? 1 : 2, inverse)) return -1;
+      const double hs = std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+      for (Engine *Ep : engs) Ep->post_s[s == STEP_PHASE1 ? 0 : 1] = hs;
       continue;
     }
     for (size_t k = 0; k < engs.size(); ++k) {
@@ -971,7 +976,7 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
   std::vector<bool> on_host(engs.size(), false);
   for (size_t k = 0; k < engs.size(); ++k) {
     Engine &E = *engs[k];
-    E.launches = 0; E.timed.clear(); E.event_next = 0;
+    E.launches = 0; E.timed.clear(); E.event_next = 0; E.post_s[0] = E.post_s[1] = 0.0;
     for (double &m : E.stage_ms) m = 0.0;
     cudaPointerAttributes attr;
     cudaError_t pe = cudaPointerGetAttributes(&attr, arrays[k]);
@@ -993,9 +998,9 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
         else cudaGetLastError();   // already pinned by the caller, or not pinnable: plain copies still work
       }
       cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
+      if (E.stage_timing && !E.async) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
       OFFTB_CUDA(cudaMemcpyAsync(E.d_user, arrays[k], bytes, cudaMemcpyHostToDevice, sc));
-      if (E.stage_timing) { cudaEventRecord(e1, sc); E.timed.push_back({ST_H2D, {e0, e1}}); }
+      if (e1) { cudaEventRecord(e1, sc); E.timed.push_back({ST_H2D, {e0, e1}}); }
       bufs[k].U = E.d_user;
     } else {
       bufs[k].U = arrays[k];
@@ -1007,9 +1012,9 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
     Engine &E = *engs[k];
     if (!on_host[k]) continue;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (E.stage_timing) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
+    if (E.stage_timing && !E.async) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, sc); }
     OFFTB_CUDA(cudaMemcpyAsync(arrays[k], E.d_user, (size_t)E.alloc * E.esz, cudaMemcpyDeviceToHost, sc));
-    if (E.stage_timing) { cudaEventRecord(e1, sc); E.timed.push_back({ST_D2H, {e0, e1}}); }
+    if (e1) { cudaEventRecord(e1, sc); E.timed.push_back({ST_D2H, {e0, e1}}); }
   }
   OFFTB_CUDA(cudaEventRecord(E0.ev_end, sc));
   if (E0.async) return 0;

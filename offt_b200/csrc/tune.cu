@@ -1,14 +1,28 @@
-// Built-in search over the reference's tunables on the device.
+// Search over the reference's tunables on the device.
 //
-// Keeps the shape of ah_tuning (offt-tuning.c:879-1006): candidate -> ADJUST_POINT repair
-// (:90-118) -> feasibility (:144-226) -> point database lookup (:231-263) -> one measured
-// execute per point (TUNING_REPS = 1, :966) -> report -> install the best point (:995-1006).
-// The candidates come from a coordinate descent on the reference's value grid over the knobs
-// that change the GPU schedule - tile thickness T (message size / launch count) and window W
-// (ring depth) of each phase - instead of from the Active Harmony server; P1 stays what the
-// plan was created with because the caller's array is already laid out for it.
+// Keeps the shape of ah_tuning (offt-tuning.c:744-1022): a candidate in grid-index space -> params_convert with its
+// ADJUST_POINT repairs (:80-136) -> feasibility (:144-226) -> point database lookup (:231-263) -> build the layout and
+// the engine for the point (:929-948) -> one measured execute on zeroed data (TUNING_REPS = 1, :958-966) -> report ->
+// install the best point (:995-1006).  Infeasible points and database hits cost no measurement and do not count
+// against max_loop; ten times max_loop fetches end the search regardless (:893).
+//
+// What proposes the candidates - in the reference an Active Harmony server with its strategy plug-ins, reached over
+// TCP - is built in (SURVEY.md section 8 keeps the server out of scope):
+//   strategy 0 / 1  Nelder-Mead over all 24 index coordinates, started from the reference's own initial simplex
+//                   (write_initial_simplex, offt-tuning.c:426-737; its patched nm.so does the same, strategies/nm.c:369-396)
+//   strategy 2      uniformly random grid points (random.so)
+//   strategy 3      coordinate descent along the tunables that change the GPU schedule, from the default point
+// Every rank runs the same deterministic search on times agreed over the world (the slowest rank's), so no broadcast
+// of the point is needed.  P1 is searched like any other tunable when the caller allows it: every trial rebuilds the
+// layout descriptor and runs on an internal zeroed device array, like the reference's memset(in, 0) (:958).
+//
+// Tunables that do nothing on a GPU - the CPU cache sub-tile sizes and the MPI_Test frequencies - stay in the point
+// (the reference's space has 24 coordinates) but are pulled into range before the feasibility test and left out of the
+// database key, so that points differing only in them are measured once.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -17,7 +31,15 @@
 
 namespace offtb {
 
+extern int g_default_precision;
+static int g_default_precision_of(const struct _offt_plan *po) {
+  return po && po->b200 ? ((Engine *)po->b200)->prec : g_default_precision;
+}
+
 namespace {
+
+const int kLive[] = {_P1_, _T1_, _W1_, _Ry_, _T2_, _W2_, _V_, _S_};   // what changes the schedule, the layout or the exchange
+const double kInfeasible = 99999999.0;                                // what the reference reports for such points (:906)
 
 // every rank must take the same decisions: agree on the slowest rank's time
 double agree_max(double x) {
@@ -45,12 +67,232 @@ void repair_ignored(int Nx, int Ny, int Nz, int p, int *v) {
   for (int i : {_Fz_, _FP1_, _FU1_, _Fy1_, _Fy2_, _FP2_, _FU2_, _Fx_}) v[i] = 0;
 }
 
-bool rebuild(struct _offt_plan *po, const int *v) {
-  engine_destroy(po);
-  memcpy(po->params->v, v, sizeof(int) * PARAM_COUNT);
-  offt_comm_free(po->comm);
-  po->comm = offt_comm_malloc(po);
-  return engine_create(po) == 0;
+struct Search {
+  struct _offt_plan *po;
+  int Nx, Ny, Nz, p;         // Nz: the z extent the tunables are sized by (Nz/2+1 for real-to-complex plans)
+  bool search_p1, verbose;
+  int max_loop;
+  std::vector<std::vector<int>> grid;
+  std::map<std::vector<int>, double> database;   // the reference's tmp-db file, kept in memory, keyed by the live tunables
+  int measured = 0, fetched = 0;
+  std::vector<int> best_v;
+  double best_t = 1e300;
+  int fixed_p1;
+  bool dead = false;         // a rebuild failed in a way the search cannot continue from
+
+  bool budget_left() const { return !dead && measured < max_loop && fetched < 10 * max_loop; }
+
+  std::vector<int> values_of(const std::vector<int> &idx) const {
+    std::vector<int> v(PARAM_COUNT);
+    for (int i = 0; i < PARAM_COUNT; ++i) {
+      const int n = (int)grid[i].size();
+      v[i] = grid[i][std::min(std::max(idx[i], 0), n - 1)];
+    }
+    return v;
+  }
+  std::vector<int> index_of(const std::vector<int> &v) const {
+    std::vector<int> idx(PARAM_COUNT, 0);
+    for (int i = 0; i < PARAM_COUNT; ++i) {
+      int bi = 0;
+      for (int c = 0; c < (int)grid[i].size(); ++c)
+        if (std::abs(grid[i][c] - v[i]) < std::abs(grid[i][bi] - v[i])) bi = c;
+      idx[i] = bi;
+    }
+    return idx;
+  }
+
+  bool rebuild(const int *v) {
+    engine_destroy(po);
+    memcpy(po->params->v, v, sizeof(int) * PARAM_COUNT);
+    offt_comm_free(po->comm);
+    po->comm = offt_comm_malloc(po);
+    return engine_create(po) == 0;
+  }
+
+  // one point: repaired, tested, looked up, measured.  Returns its time in seconds (kInfeasible if it cannot run).
+  double evaluate(std::vector<int> v) {
+    ++fetched;
+    if (!search_p1) v[_P1_] = fixed_p1;
+    params_adjust(Nx, Ny, Nz, p, po->is_oned, v.data());
+    repair_ignored(Nx, Ny, Nz, p, v.data());
+    if (po->is_W0) v[_W1_] = v[_W2_] = 0;
+    int bad;
+    // the ring-size rule of the reference is about MPI_Alloc_mem on its clusters; HBM has room for far larger rings,
+    // so only the structural rules decide here - and the memory actually free on the device (below)
+    if (params_infeasible(Nx, Ny, Nz, p, v.data(), &bad) && bad != _W1_ && bad != _W2_) {
+      if (verbose) { printf("INFEASIBLE POINT err_i:%d ", bad); print_params(v.data()); }
+      return kInfeasible;
+    }
+    auto cd = [](int a, int b) { return (a + b - 1) / b; };
+    const int p1 = v[_P1_], p2 = p / p1;
+    const long long M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(Nz, p2), M4 = cd(Ny, p1);
+    if (v[_W1_] > cd((int)M1, v[_T1_]) || v[_W2_] > cd((int)M3, v[_T2_])) return kInfeasible;
+    std::vector<int> key;
+    for (int k : kLive) key.push_back(v[k]);
+    auto it = database.find(key);
+    if (it != database.end()) {
+      if (verbose) { printf("%.5f FOUND IN DATABASE ", it->second); print_params(v.data()); }
+      return it->second;
+    }
+    // a cheap upper bound on what the point allocates (rings, scratch, the trial array) against the memory that is
+    // free right now: a point that cannot fit is infeasible for everybody, before any collective is entered
+    {
+      const size_t esz = g_default_precision_of(po) == PREC_F64 ? 16 : 8;
+      const bool ph1 = !(po->is_oned && p1 == p) && p > 1, ph2 = !(po->is_oned && p1 == 1) && p > 1;
+      const long long ring = (ph1 ? 2LL * v[_T1_] * M2 * M3 * p2 * (v[_W1_] + 1) : 0) + (ph2 ? 2LL * M1 * M4 * p1 * v[_T2_] * (v[_W2_] + 1) : 0);
+      const long long arrays = 2 * std::max(M2 * p2, M4 * p1) * M1 * M3;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      Engine *cur = (Engine *)po->b200;
+      size_t mine = 0;   // what the current engine holds is released before the point is built
+      if (cur) mine = ((size_t)cur->alloc * (cur->d_scratch ? 1 : 0) + (size_t)(cur->ring[0].slot_elems * 2 * cur->ring[0].depth + cur->ring[1].slot_elems * 2 * cur->ring[1].depth)) * esz;
+      const double fits = agree_max((double)((size_t)(ring + arrays) * esz > free_b + mine ? 1 : 0));
+      if (fits > 0) {
+        if (verbose) { printf("INFEASIBLE POINT (device memory) "); print_params(v.data()); }
+        database[key] = kInfeasible;
+        return kInfeasible;
+      }
+    }
+    if (!rebuild(v.data())) {
+      // all ranks fail together (engine_create agrees on allocation failures): the point is infeasible, the search goes on
+      if (verbose) { printf("INFEASIBLE POINT (%s) ", last_error()); print_params(v.data()); }
+      database[key] = kInfeasible;
+      if (!po->b200 && !rebuild(best_v.empty() ? v.data() : best_v.data()) && best_v.empty()) dead = true;
+      return kInfeasible;
+    }
+    Engine *E = (Engine *)po->b200;
+    void *trial = nullptr;
+    const size_t bytes = (size_t)E->alloc * E->esz;
+    const double ok = agree_max(cudaMalloc(&trial, bytes) == cudaSuccess ? 0.0 : 1.0);
+    if (ok > 0) {
+      cudaGetLastError();
+      if (trial) cudaFree(trial);
+      database[key] = kInfeasible;
+      return kInfeasible;
+    }
+    double t = 1e30;
+    const bool was_timing = E->stage_timing;
+    E->stage_timing = false;
+    for (int rep = 0; rep < 1 + TUNING_REPS; ++rep) {   // one warm-up, then the measured run(s), best of them (:966)
+      cudaMemset(trial, 0, bytes);                       // the reference tunes on zeros too (:958)
+      offtb_world_barrier();
+      offt_3d_execute(po, (double *)trial, (double *)trial, 1);
+      if (rep > 0) t = std::min(t, po->t[ALL]);
+    }
+    E->stage_timing = was_timing;
+    cudaFree(trial);
+    t = agree_max(t);
+    database[key] = t;
+    ++measured;
+    if (verbose) { printf("@ TUNE %.6f ", t); print_params(v.data()); }
+    if (t < best_t) { best_t = t; best_v = v; }
+    return t;
+  }
+};
+
+// ---- strategy 0 / 1: Nelder-Mead in index space from the reference's initial simplex -----------------------------
+void search_nelder_mead(Search &S) {
+  const int D = PARAM_COUNT, NV = PARAM_COUNT + 1;
+  std::vector<int *> v_list(D);
+  std::vector<int> v_size(D);
+  for (int i = 0; i < D; ++i) { v_list[i] = S.grid[i].data(); v_size[i] = (int)S.grid[i].size(); }
+  int x0[PARAM_COUNT + 1][PARAM_COUNT];
+  srand(20161);   // the same vertices on every rank (the reference draws them on rank 0 and broadcasts the points)
+  initial_simplex(S.Nx, S.Ny, S.Nz, S.p, S.po->is_oned, S.po->is_W0, S.po->is_notest, S.search_p1 ? S.po->tuning_mode : 0, v_list.data(), v_size.data(), x0);
+  std::vector<std::vector<double>> X(NV, std::vector<double>(D));
+  std::vector<double> F(NV);
+  auto eval = [&](const std::vector<double> &x) {
+    std::vector<int> idx(D);
+    for (int i = 0; i < D; ++i) idx[i] = (int)std::lround(std::min(std::max(x[i], 0.0), (double)(v_size[i] - 1)));
+    return S.evaluate(S.values_of(idx));
+  };
+  for (int k = 0; k < NV && S.budget_left(); ++k) {
+    for (int i = 0; i < D; ++i) X[k][i] = x0[k][i];
+    F[k] = eval(X[k]);
+  }
+  std::vector<int> order(NV);
+  while (S.budget_left()) {
+    for (int k = 0; k < NV; ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return F[a] < F[b]; });
+    const int lo = order[0], hi = order[NV - 1], nhi = order[NV - 2];
+    // converged: every vertex rounds to the same point
+    bool same = true;
+    for (int k = 1; k < NV && same; ++k)
+      for (int i = 0; i < D && same; ++i) same = std::lround(X[order[k]][i]) == std::lround(X[lo][i]);
+    if (same) break;
+    std::vector<double> c(D, 0.0);
+    for (int k = 0; k < NV; ++k) if (k != hi) for (int i = 0; i < D; ++i) c[i] += X[k][i] / (NV - 1);
+    auto along = [&](double a) { std::vector<double> y(D); for (int i = 0; i < D; ++i) y[i] = c[i] + a * (X[hi][i] - c[i]); return y; };
+    std::vector<double> xr = along(-1.0);
+    const double fr = eval(xr);
+    if (fr < F[lo]) {
+      std::vector<double> xe = along(-2.0);
+      const double fe = S.budget_left() ? eval(xe) : kInfeasible;
+      if (fe < fr) { X[hi] = xe; F[hi] = fe; } else { X[hi] = xr; F[hi] = fr; }
+    } else if (fr < F[nhi]) {
+      X[hi] = xr; F[hi] = fr;
+    } else {
+      std::vector<double> xc = along(fr < F[hi] ? -0.5 : 0.5);
+      const double fc = S.budget_left() ? eval(xc) : kInfeasible;
+      if (fc < std::min(fr, F[hi])) { X[hi] = xc; F[hi] = fc; }
+      else {
+        for (int k = 0; k < NV && S.budget_left(); ++k) {   // shrink towards the best vertex
+          if (k == lo) continue;
+          for (int i = 0; i < D; ++i) X[k][i] = X[lo][i] + 0.5 * (X[k][i] - X[lo][i]);
+          F[k] = eval(X[k]);
+        }
+      }
+    }
+  }
+}
+
+// ---- strategy 2: random grid points -------------------------------------------------------------------------------
+void search_random(Search &S) {
+  unsigned long long state = 0x9E3779B97F4A7C15ULL;
+  auto next = [&]() { state = state * 6364136223846793005ULL + 1442695040888963407ULL; return (unsigned)(state >> 33); };
+  std::vector<int> v(PARAM_COUNT);
+  S.evaluate(std::vector<int>(S.po->params->v, S.po->params->v + PARAM_COUNT));
+  while (S.budget_left()) {
+    for (int i = 0; i < PARAM_COUNT; ++i) v[i] = S.grid[i][next() % S.grid[i].size()];
+    S.evaluate(v);
+  }
+}
+
+// ---- strategy 3: coordinate descent along the live tunables ---------------------------------------------------------
+void search_coordinate(Search &S) {
+  std::vector<int> best(S.po->params->v, S.po->params->v + PARAM_COUNT);
+  double best_t = S.evaluate(best);
+  if (best_t >= kInfeasible) return;
+  bool improved = true;
+  while (improved && S.budget_left()) {
+    improved = false;
+    for (int k : kLive) {
+      if (k == _P1_ && !S.search_p1) continue;
+      if (k == _V_) continue;   // exact counts change nothing a fused exchange can measure
+      const std::vector<int> &g = S.grid[k];
+      auto pos = std::find(g.begin(), g.end(), best[k]);
+      if (pos == g.end()) pos = g.begin() + S.index_of(best)[k];
+      for (int dir : {+1, -1}) {
+        std::vector<int> cur = best;
+        auto q = pos;
+        while (S.budget_left()) {
+          if (dir > 0) { if (q + 1 == g.end()) break; ++q; } else { if (q == g.begin()) break; --q; }
+          cur[k] = *q;
+          if (k == _P1_) {   // another decomposition: start from that decomposition's default tiles (M/16, window 2; offt-compute.c:3147-3175)
+            const int p1 = cur[_P1_], p2 = S.p / p1;
+            auto snap = [&](int knob, int raw) { int b = S.grid[knob][0]; for (int c : S.grid[knob]) if (c <= raw) b = c; return b; };
+            cur[_T1_] = snap(_T1_, std::max(1, (S.Nx + p1 - 1) / p1 / 16));
+            cur[_T2_] = snap(_T2_, std::max(1, (S.Nz + p2 - 1) / p2 / 16));
+            cur[_W1_] = cur[_W2_] = S.po->is_W0 ? 0 : 2;
+            cur[_Ry_] = 5;
+          }
+          const double t = S.evaluate(cur);
+          if (t >= kInfeasible) { if (k == _P1_) continue; break; }
+          if (t < best_t) { best_t = t; best = S.best_v.empty() ? cur : S.best_v; improved = true; pos = q; } else break;
+        }
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -59,73 +301,43 @@ bool rebuild(struct _offt_plan *po, const int *v) {
 
 using namespace offtb;
 
-extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose) {
+// strategy: 0 / 1 Nelder-Mead from the reference's initial simplex, 2 random, 3 coordinate descent (see the header
+// comment); search_p1: also search the decomposition (the caller must not have laid out its array for one yet).
+// Returns the number of points measured, or a negative code.
+extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1) {
   if (!po || !po->b200) { set_error("null plan"); return -1; }
   if (world().local && world().size > 1) { set_error("tuning runs one rank per process"); return -1; }
-  (void)in;
-  const int Nx = po->Nx, Ny = po->Ny, Nz = po->is_r2c ? po->Nz / 2 + 1 : po->Nz, p = po->p;   // offt-tuning.c:110, 161
-  const auto grid = params_grid(Nx, Ny, Nz, p);
-  std::vector<int> best(po->params->v, po->params->v + PARAM_COUNT);
-  params_adjust(Nx, Ny, Nz, p, po->is_oned, best.data());
-  repair_ignored(Nx, Ny, Nz, p, best.data());
-  std::map<std::vector<int>, double> database;   // the reference's tmp-db file, kept in memory
-  int evaluated = 0;
-
-  auto measure = [&](std::vector<int> v) -> double {
-    params_adjust(Nx, Ny, Nz, p, po->is_oned, v.data());
-    repair_ignored(Nx, Ny, Nz, p, v.data());
-    int bad;
-    // the ring-size rule of the reference is about MPI_Alloc_mem on its clusters; HBM has room
-    // for far larger rings, so only the structural rules decide here
-    if (params_infeasible(Nx, Ny, Nz, p, v.data(), &bad) && bad != _W1_ && bad != _W2_) return -1.0;
-    if (v[_W1_] > (po->comm->M1 + v[_T1_] - 1) / v[_T1_] || v[_W2_] > (po->comm->M3 + v[_T2_] - 1) / v[_T2_]) return -1.0;
-    auto it = database.find(v);
-    if (it != database.end()) return it->second;
-    if (!rebuild(po, v.data())) return -1.0;
-    double t = 1e30;
-    for (int rep = 0; rep < 1 + TUNING_REPS; ++rep) {   // one warm-up, then the measured run
-      offt_3d_execute(po, out, out, 1);
-      t = po->t[ALL];
-    }
-    t = agree_max(t);
-    database[v] = t;
-    ++evaluated;
-    if (verbose) { printf("@ TUNE %.6f ", t); print_params(v.data()); }
-    return t;
-  };
-
-  double best_t = measure(best);
-  if (best_t < 0) { set_error("the starting point is infeasible"); return -1; }
-  const int knobs[4] = {_T1_, _W1_, _T2_, _W2_};
-  bool improved = true;
-  while (improved && evaluated < max_loop) {
-    improved = false;
-    for (int k : knobs) {
-      // a slab schedule has only one live phase
-      Engine *E = (Engine *)po->b200;
-      if ((k == _T1_ || k == _W1_) && E->sched == SCHED_SLAB_PX1) continue;
-      if ((k == _T2_ || k == _W2_) && E->sched == SCHED_SLAB_1XP) continue;
-      if (E->sched == SCHED_SINGLE) continue;
-      const std::vector<int> &g = grid[k];
-      auto pos = std::find(g.begin(), g.end(), best[k]);
-      for (int dir : {+1, -1}) {
-        std::vector<int> cur = best;
-        auto q = pos;
-        while (evaluated < max_loop) {
-          if (q == g.end()) break;
-          if (dir > 0) { if (q + 1 == g.end()) break; ++q; } else { if (q == g.begin()) break; --q; }
-          cur[k] = *q;
-          const double t = measure(cur);
-          if (t < 0) break;
-          if (t < best_t) { best_t = t; best = cur; improved = true; pos = q; } else break;
-        }
-      }
-    }
+  (void)in; (void)out;   // trials run on an internal zeroed device array (offt-tuning.c:958 zeroes the caller's)
+  Search S;
+  S.po = po;
+  S.Nx = po->Nx; S.Ny = po->Ny; S.Nz = po->is_r2c ? po->Nz / 2 + 1 : po->Nz; S.p = po->p;   // offt-tuning.c:110, 161
+  S.search_p1 = search_p1 != 0 && po->p > 1;
+  S.verbose = verbose != 0;
+  S.max_loop = max_loop;
+  S.grid = params_grid(S.Nx, S.Ny, S.Nz, S.p);
+  S.fixed_p1 = po->params->v[_P1_];
+  if (S.search_p1 && po->tuning_mode == 1) { S.search_p1 = false; S.fixed_p1 = 1; }
+  if (S.search_p1 && po->tuning_mode == 2) { S.search_p1 = false; S.fixed_p1 = po->p; }
+  const std::vector<int> start(po->params->v, po->params->v + PARAM_COUNT);
+  if (((Engine *)po->b200)->sched == SCHED_SINGLE && !S.search_p1) max_loop = S.max_loop = std::min(max_loop, 2);   // one rank: nothing to search but S
+  switch (strategy) {
+    case 0: case 1: search_nelder_mead(S); break;
+    case 2: search_random(S); break;
+    default: search_coordinate(S); break;
   }
-  params_adjust(Nx, Ny, Nz, p, po->is_oned, best.data());
-  repair_ignored(Nx, Ny, Nz, p, best.data());
-  if (!rebuild(po, best.data())) return -1;
+  if (S.best_v.empty()) {
+    // nothing feasible was measured: put the plan back where it started
+    std::vector<int> v = start;
+    if (!po->b200 && !S.rebuild(v.data())) { set_error("tuning found no feasible point and could not restore the plan: %s", last_error()); return -1; }
+    set_error("the search found no feasible point");
+    return -1;
+  }
+  if (!S.rebuild(S.best_v.data())) return -1;
   po->params->is_converged = 1;
-  if (verbose) { printf("@ BEST %.6f ", best_t); print_params(po->params->v); }
-  return evaluated;
+  if (verbose) { printf("@ BEST "); print_params(po->params->v); printf("@ BEST %.5f\n", S.best_t); }
+  return S.measured;
+}
+
+extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose) {
+  return offtb_tune_ex(po, in, out, max_loop, verbose, 3, 0);
 }

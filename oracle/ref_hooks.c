@@ -7,7 +7,9 @@
  *   params_range_setup (offt-compute.c:2998), params_set_default (:3127), grid_value_floor/ceil (:3096, :3111),
  *   params_convert (offt-tuning.c:80), is_infeasible_point (offt-tuning.c:144).
  *
- * usage: ref_hooks Nx Ny Nz p is_oned is_W0 is_notest npoints seed
+ * usage: ref_hooks Nx Ny Nz p is_oned is_W0 is_notest npoints seed [simplex_seed tuning_mode is_r2c]
+ *        with the three optional arguments it also prints "simplex <i> <24 indices>" for the 25 vertices the reference's
+ *        write_initial_simplex (offt-tuning.c:426-737) draws after srand(simplex_seed)
  * output: "range i n v0 v1 ...", "default v0..v23", then per random index vector
  *         "point <24 indices> -> <24 values> infeasible <ret> <p_i>" and per tunable "floorceil i raw f c fi ci"
  */
@@ -15,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <mpi.h>
 #include "offt.h"
 #include "offt-internal.h"
@@ -22,6 +25,7 @@
 void params_set_default(struct _offt_plan *po);
 void params_convert(int is_backward, int *v, long *ahv, struct _offt_plan *po, int **v_list, int *v_list_size);
 int is_infeasible_point(struct _offt_plan *po, int *v, int *p_i);
+void write_initial_simplex(struct _offt_plan *po, int **v_list, int *v_list_size);
 
 static uint64_t mix(uint64_t seed, uint64_t index) {
   uint64_t z = seed * 0x9E3779B97F4A7C15ULL + index * 0xD1B54A32D192ED03ULL + 0x632BE59BD9B4E019ULL;
@@ -38,6 +42,7 @@ int main(int argc, char **argv) {
   const int npoints = atoi(argv[8]);
   const uint64_t seed = strtoull(argv[9], NULL, 10);
   po->params = (struct _offt_params *)calloc(1, sizeof(struct _offt_params));
+  if (argc >= 13) { po->tuning_mode = atoi(argv[11]); po->is_r2c = atoi(argv[12]); }
   int *v_list[PARAM_COUNT];
   int v_list_size[PARAM_COUNT];
   int i, k;
@@ -70,6 +75,16 @@ int main(int argc, char **argv) {
       printf("floorceil %d %d %d %d %d %d\n", i, probes[k], grid_value_floor(0, v_list, v_list_size, i, probes[k]),
              grid_value_ceil(0, v_list, v_list_size, i, probes[k]), grid_value_floor(1, v_list, v_list_size, i, probes[k]),
              grid_value_ceil(1, v_list, v_list_size, i, probes[k]));
+  }
+  if (argc >= 13) {
+    char line[4096];
+    snprintf(po->user_vertex_file, sizeof(po->user_vertex_file), "/tmp/ref_hooks_uv_%d", (int)getpid());
+    srand((unsigned)atoi(argv[10]));
+    write_initial_simplex(po, v_list, v_list_size);
+    FILE *f = fopen(po->user_vertex_file, "r");
+    for (i = 0; f && fgets(line, sizeof(line), f); i++) printf("simplex %d %s", i, line);
+    if (f) fclose(f);
+    remove(po->user_vertex_file);
   }
   /* the two printers of the public API (offt.h:243-244), on fixed inputs */
   {

@@ -108,6 +108,31 @@ def main():
         ok = same and on_grid and e < 1e-12 and trials >= 1
         failures += 0 if ok else 1
         print(f"{'ok  ' if ok else 'FAIL'} tuning: {trials} trials -> T2 {tuned[P.T2]} W2 {tuned[P.W2]}, same on all ranks {same}, on grid {on_grid}, vs numpy {e:.2e}", flush=True)
+    # the same loop searching the decomposition too, Nelder-Mead from the reference's initial simplex (ah_strategy 0): P1 may
+    # change, so the layout is read only afterwards (run-fft.c:314 -> :269-304) and the transform must still be right
+    N, oned = (64, 128, 64), 0
+    grid = O.grid_values(4, *N)
+    plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom={P.P1: 1})
+    trials = plan.tune_ex(10, strategy=0, search_p1=True)
+    tuned = plan.params
+    box = box_of(plan, N, world)
+    arr = torch.from_numpy(np.ascontiguousarray(O.scatter_input(box, grid))).to(dev)
+    plan.execute(arr)
+    fwd = arr.cpu().numpy()
+    plan.fin()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (box, fwd, tuned))
+    if rank == 0:
+        boxes = []
+        for b, f, _ in gathered:
+            b.data = f
+            boxes.append(b)
+        same = all(g[2] == tuned for g in gathered)
+        e = O.rel_l2(O.gather_output(boxes), np.fft.fftn(grid))
+        ok = same and e < 1e-12 and trials >= 1
+        failures += 0 if ok else 1
+        print(f"{'ok  ' if ok else 'FAIL'} tuning incl. P1 (Nelder-Mead): {trials} trials -> P1 {tuned[P.P1]} T1 {tuned[P.T1]} W1 {tuned[P.W1]} T2 {tuned[P.T2]} W2 {tuned[P.W2]} S {tuned[P.S]}, "
+              f"same on all ranks {same}, vs numpy {e:.2e}", flush=True)
     ob.world_fin()
     ft = torch.tensor([failures], device=dev)
     dist.broadcast(ft, 0)

@@ -383,3 +383,29 @@ def test_r2c_matches_numpy_and_round_trips(N, p, oned, custom, bits):
     if bits == 32:
         back = [b.view(np.float32).astype(np.float64).view(np.complex128) for b in back]
     assert O.rel_l2(O.gather_input_r2c(got, back) / np.prod(N), grid.real) < TOL[bits]
+
+
+def test_timer_buckets_are_filled_by_default():
+    """po->t[] (offt.h:171-188), what run-fft.c prints per repetition (run-fft.c:399-413): ALL and the four FFT
+    buckets carry device time after every execute without any opt-in; the fused-away steps stay zero"""
+    torch = _torch()
+    import offt_b200 as ob
+    ALL, INIT1, WAIT1, TEST1, INIT2, WAIT2, TEST2, FFTz, FFTy1, FFTy2, FFTx, TRANSPOSE, PACK1, UNPACK1, PACK2, UNPACK2 = range(16)
+    N = (64, 64, 64)
+    with local_world(1):
+        plan = ob.Plan(*N, is_notest=1, custom={P.P1: 1})
+        a = torch.zeros(plan.alloc_elems, dtype=torch.complex128, device="cuda")
+        plan.execute(a)
+        t = plan.t
+        assert t[ALL] > 0 and t[FFTz] > 0 and t[FFTy1] > 0 and t[FFTx] > 0
+        assert t[FFTz] + t[FFTy1] + t[FFTy2] + t[FFTx] <= t[ALL] * 1.05
+        assert t[TRANSPOSE] == 0 and t[PACK1] == 0 and t[TEST1] == 0
+        plan.fin()
+    with local_world(4):
+        plans = [ob.Plan(*N, is_notest=1, custom={P.P1: 2}, rank=r) for r in range(4)]
+        arrs = [torch.zeros(pl.alloc_elems, dtype=torch.complex128, device="cuda") for pl in plans]
+        ob.execute_group(plans, arrs)
+        t = plans[0].t
+        assert all(t[k] > 0 for k in (ALL, FFTz, FFTy1, FFTy2, FFTx, INIT1, INIT2))
+        for pl in plans:
+            pl.fin()

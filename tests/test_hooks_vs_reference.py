@@ -127,3 +127,38 @@ def test_hooks_match_the_reference_functions(cfg):
                lib.grid_value_floor(1, lists, sizes, i, raw), lib.grid_value_ceil(1, lists, sizes, i, raw))
         assert got == (fv, cv, fi, ci), f"grid_value_floor/ceil of tunable {i} at {raw}"
     assert ob  # the binding loaded the product library
+
+
+SIMPLEX_CONFIGS = [  # (Nx Ny Nz p is_oned is_W0 is_notest), tuning_mode, is_r2c, seed
+    ((64, 32, 128, 4, 0, 0, 1), 0, 0, 7), ((256, 256, 256, 4, 1, 0, 0), 0, 0, 11), ((1024, 1024, 1024, 8, 1, 0, 1), 2, 0, 3),
+    ((2048, 2048, 2048, 8, 0, 0, 1), 0, 0, 5), ((2048, 1024, 512, 8, 1, 1, 1), 0, 0, 9), ((2048, 1024, 512, 8, 1, 0, 1), 1, 0, 13),
+    ((512, 512, 512, 64, 0, 0, 0), 0, 0, 2), ((64, 32, 130, 4, 0, 0, 1), 0, 1, 21), ((16, 8, 32, 2, 1, 0, 1), 0, 0, 1),
+]
+
+
+@pytest.mark.skipif(not HOOKS.exists(), reason="oracle/_ref/ref_hooks not built (needs /root/reference)")
+@pytest.mark.parametrize("cfg,mode,r2c,seed", SIMPLEX_CONFIGS)
+def test_initial_simplex_matches_reference(cfg, mode, r2c, seed, tmp_path):
+    """write_initial_simplex (offt-tuning.c:426-737): with the same srand() seed the library draws the same 25 vertices,
+    coordinate by coordinate, as the unmodified reference function - for every tuning mode, r2c, is_W0 and is_notest"""
+    import offt_b200 as ob
+    out = subprocess.run([str(HOOKS)] + [str(v) for v in cfg] + ["0", "1", str(seed), str(mode), str(r2c)],
+                         capture_output=True, text=True, timeout=120, check=True).stdout
+    want = [[int(x) for x in line.split()[2:]] for line in out.splitlines() if line.startswith("simplex")]
+    assert len(want) == 25 and all(len(w) == 24 for w in want)
+    po = ob.binding.OfftPlan()
+    po.Nx, po.Ny, po.Nz, po.p, po.is_oned, po.is_W0, po.is_notest = cfg
+    po.tuning_mode, po.is_r2c = mode, r2c
+    po.user_vertex_file = str(tmp_path / "uv").encode()
+    lib = ob.lib
+    v_list = (C.POINTER(C.c_int) * 24)()
+    v_size = (C.c_int * 24)()
+    lib.params_range_setup.argtypes = [C.POINTER(ob.binding.OfftPlan), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_int)]
+    lib.params_range_setup.restype = None
+    lib.write_initial_simplex.argtypes = lib.params_range_setup.argtypes
+    lib.write_initial_simplex.restype = None
+    lib.params_range_setup(C.byref(po), v_list, v_size)
+    C.CDLL(None).srand(seed)
+    lib.write_initial_simplex(C.byref(po), v_list, v_size)
+    got = [[int(x) for x in line.split()] for line in (tmp_path / "uv").read_text().splitlines()]
+    assert got == want
