@@ -104,9 +104,11 @@ long long offtb_exchange_block_elems(const struct _offt_plan *po, int phase, int
 int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose);
 /* the same with the candidate source spelled out.  strategy: 0 / 1 Nelder-Mead over all 24 index coordinates from the
  * reference's initial simplex (write_initial_simplex, offt-tuning.c:426-737), 2 random grid points, 3 coordinate descent
- * along the tunables that change the GPU schedule (what offtb_tune does).  search_p1 != 0 also searches the
- * decomposition _P1_ - every trial then rebuilds the layout descriptor (offt-tuning.c:929-948), so the caller must read
- * po->comm only afterwards, as run-fft.c does.  Trials run on an internal zeroed device array. */
+ * along the tunables that change the GPU schedule (what offtb_tune does).  search_p1 != 0 also searches what
+ * changes the caller's layout - the decomposition _P1_ and the output order _S_; every trial then rebuilds the layout
+ * descriptor (offt-tuning.c:929-948), so the caller must read po->comm only afterwards, as run-fft.c does.  Without it
+ * only tile sizes, windows and _Ry_ move and istride / ostride stay what they were.  Trials run on an internal zeroed
+ * device array. */
 int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1);
 /* offt-tuning.c:426-737: writes the 25 starting vertices (grid indices) of the Nelder-Mead search to po->user_vertex_file */
 void write_initial_simplex(struct _offt_plan *po, int **v_list, int *v_list_size);

@@ -84,12 +84,17 @@ struct Ring {
 };
 
 // Flag words of the fused exchange, one block per rank in an IPC-shared allocation.  Peers write them over NVLink.
-//   arrived[phase][j]  : group member j has stored its block of tile number arrived into my landing slot
-//   released[phase][j] : group member j has finished reading the tile number it stored from/into its slot
+//   arrived[phase][slot][j]  : group member j has stored its block of tile number `arrived` into my landing slot `slot`
+//   released[phase][slot][j] : group member j has finished reading tile number `released` out of its slot `slot`
 #define OFFTB_DONE_SLOTS 32
+#define OFFTB_MAX_SLOTS 65   // ring depth W + 1 with W <= 64
+// One word per (phase, ring slot, group member): the launches of a dependent-launch chain run concurrently and may
+// finish out of order, so tile s and tile s+1 must not announce themselves through the same word (a later tile's
+// number overwritten by an earlier tile's would make the word go backwards, and ">= s" would no longer mean "s is
+// complete").  A slot's tenants s, s+depth, ... are ordered by the protocol itself, so each word only ever grows.
 struct XFlags {
-  unsigned arrived[2][OFFTB_MAX_GROUP];
-  unsigned released[2][OFFTB_MAX_GROUP];
+  unsigned arrived[2][OFFTB_MAX_SLOTS][OFFTB_MAX_GROUP];
+  unsigned released[2][OFFTB_MAX_SLOTS][OFFTB_MAX_GROUP];
   // [phase][writer, reader][tile number mod OFFTB_DONE_SLOTS]: launches of a dependent-launch chain overlap, so
   // consecutive tiles count their finished CTAs in different words
   unsigned done_counter[2][2][OFFTB_DONE_SLOTS];

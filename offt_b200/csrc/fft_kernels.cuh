@@ -542,6 +542,9 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
     if (tid < 32) bulk_store_wait_all();   // every run has reached its destination
   }
   cp_async_wait(0);
+  // A launch that was allowed to start before its predecessor had drained must not FINISH before it either: whatever
+  // follows the chain on the stream (an event, the next phase, the caller's own kernels) waits only for the last launch.
+  if ((a.pdl & 2) && tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.signal_count > 0) {
     // every store of this CTA is ordered before the counter; the last CTA tells the peers
     __threadfence_system();

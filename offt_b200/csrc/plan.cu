@@ -592,12 +592,12 @@ int fuse_writer(std::vector<Engine *> &engs, Engine &E, Launch &L, int phase, in
   if (!w.local) {
     const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
     if (R.tiles_done + (unsigned long long)tile >= (unsigned long long)R.depth) {
-      L.wait_flags = E.d_flags->released[phase - 1];
+      L.wait_flags = E.d_flags->released[phase - 1][slot];
       L.wait_count = (int)members.size();
       L.wait_value = seq - (unsigned)R.depth;
     }
     for (size_t j = 0; j < members.size(); ++j)
-      L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][me];
+      L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->arrived[phase - 1][slot][me];
     L.signal_count = (int)members.size();
     L.signal_value = seq;
     L.done_counter = &E.d_flags->done_counter[phase - 1][0][seq % OFFTB_DONE_SLOTS];
@@ -614,11 +614,12 @@ int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
   int me;
   group_of(E, phase, members, me);
   const unsigned seq = (unsigned)(R.tiles_done + (unsigned long long)tile + 1ULL);
-  L.wait_flags = E.d_flags->arrived[phase - 1];
+  const int slot = slot_of(R, tile);
+  L.wait_flags = E.d_flags->arrived[phase - 1][slot];
   L.wait_count = (int)members.size();
   L.wait_value = seq;
   for (size_t j = 0; j < members.size(); ++j)
-    L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][me];
+    L.signal_ptrs[j] = &((XFlags *)E.peer_flags[members[j]])->released[phase - 1][slot][me];
   L.signal_count = (int)members.size();
   L.signal_value = seq;
   L.done_counter = &E.d_flags->done_counter[phase - 1][1][seq % OFFTB_DONE_SLOTS];

@@ -77,7 +77,8 @@ struct Search {
   int measured = 0, fetched = 0;
   std::vector<int> best_v;
   double best_t = 1e300;
-  int fixed_p1;
+  int fixed_p1, fixed_S = 0;
+  bool search_layout = false;   // the decomposition P1 and the output layout S may move (nobody has read po->comm yet)
   bool dead = false;         // a rebuild failed in a way the search cannot continue from
 
   bool budget_left() const { return !dead && measured < max_loop && fetched < 10 * max_loop; }
@@ -113,6 +114,7 @@ struct Search {
   double evaluate(std::vector<int> v) {
     ++fetched;
     if (!search_p1) v[_P1_] = fixed_p1;
+    if (!search_layout) v[_S_] = fixed_S;   // the caller has read the output strides already
     params_adjust(Nx, Ny, Nz, p, po->is_oned, v.data());
     repair_ignored(Nx, Ny, Nz, p, v.data());
     if (po->is_W0) v[_W1_] = v[_W2_] = 0;
@@ -268,6 +270,7 @@ void search_coordinate(Search &S) {
     improved = false;
     for (int k : kLive) {
       if (k == _P1_ && !S.search_p1) continue;
+      if (k == _S_ && !S.search_layout) continue;
       if (k == _V_) continue;   // exact counts change nothing a fused exchange can measure
       const std::vector<int> &g = S.grid[k];
       auto pos = std::find(g.begin(), g.end(), best[k]);
@@ -302,7 +305,8 @@ void search_coordinate(Search &S) {
 using namespace offtb;
 
 // strategy: 0 / 1 Nelder-Mead from the reference's initial simplex, 2 random, 3 coordinate descent (see the header
-// comment); search_p1: also search the decomposition (the caller must not have laid out its array for one yet).
+// comment); search_p1: also search what changes the caller's layout - the decomposition P1 and the output order S
+// (the caller must not have read po->comm yet, as in the reference where tuning happens inside offt_3d_init).
 // Returns the number of points measured, or a negative code.
 extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1) {
   if (!po || !po->b200) { set_error("null plan"); return -1; }
@@ -312,6 +316,8 @@ extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int
   S.po = po;
   S.Nx = po->Nx; S.Ny = po->Ny; S.Nz = po->is_r2c ? po->Nz / 2 + 1 : po->Nz; S.p = po->p;   // offt-tuning.c:110, 161
   S.search_p1 = search_p1 != 0 && po->p > 1;
+  S.search_layout = search_p1 != 0;
+  S.fixed_S = po->params->v[_S_];
   S.verbose = verbose != 0;
   S.max_loop = max_loop;
   S.grid = params_grid(S.Nx, S.Ny, S.Nz, S.p);
