@@ -665,6 +665,13 @@ def own_arm(args):
             # configs[2]'s grid on ONE GPU: the missing point of a true strong-scaling curve (1 -> 2/4/8 GPUs on 1024^3)
             extra["strong_scaling_n1_1024"] = measure_config(cx, (1024, 1024, 1024), bits=64, oned=0, custom={P.P1: 1, P.S: 1}, steps=5,
                                                              label="1024^3 complex128 forward on one GPU (configs[2]'s grid without the exchange)")
+        if args.extra_test and world > 1:
+            # the same code path as the 8-GPU extras on grids that fit any world (validation runs of this script)
+            p1x = 2 if world >= 4 else world
+            extra_configs.append(measure_config(cx, (256, 256, 256), bits=64, oned=0 if world >= 4 else 1, custom={P.P1: p1x, P.S: 0}, steps=3,
+                                                label=f"extra-test: 256^3 complex128, P1={p1x}"))
+            extra_configs.append(measure_config(cx, (512, 256, 128), bits=32, oned=1, custom={P.P1: world, P.S: 0}, steps=3, tune=10,
+                                                label="extra-test: 512x256x128 complex64, tunables searched"))
         if world == 8 and N == (1024, 1024, 1024):
             extra_configs.append(measure_config(cx, (2048, 2048, 2048), bits=64, oned=0, custom={P.P1: 2, P.S: 0}, steps=3,
                                                 label="configs[3]: 2048^3 complex128 forward, pencil 2x4, 8 GPUs"))
@@ -717,6 +724,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gate", action="store_true", help="skip the multi-process parity gate (experiments only)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra configurations (1024^3 on one GPU; configs[3], configs[4] at 8 GPUs)")
+    ap.add_argument("--extra-test", action="store_true", help="run the extra-configuration code path on small grids (validation of this script)")
     ap.add_argument("--ref-sample", action="store_true", help="reference arm: force the bounded 512^3 sample even if the host could run the workload")
     args = ap.parse_args()
     sys.exit(reference_arm(args) if args.impl == "reference" else own_arm(args))
