@@ -202,7 +202,13 @@ cudaEvent_t pool_event(Engine &E) {
 }
 
 int pick_c_log(const Engine &E, const FftKernelInfo &info, const Launch &L) {
-  return fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, L.im.n_lo, L.om.n_lo);
+  int lg = fft_pick_c_log(info, E.prec, L.load_cfast || L.store_cfast, L.im.B0, L.nbatch, L.im.n_lo, L.om.n_lo);
+  // narrow tiles of a phase whose full-width tiles leave no room for writer and reader side by side (plan_phase_overlap)
+  if (E.narrow_now && (L.load_cfast || L.store_cfast)) {
+    const int cap = E.prec == PREC_F64 ? 1 : 2;   // 32 bytes per transform index
+    lg = std::min(lg, cap);
+  }
+  return lg;
 }
 
 // Can the launch drain its output with TMA bulk stores (fft_kernels.cuh, FftArgs::bulk_store)?  Only launches that
@@ -368,6 +374,7 @@ Launch L_k2(const Dims &d, const void *recv, void *A, long long x0, long long my
 long long z_chunk(const Engine &E, long long myT) {
   static const long long env_cz = getenv("OFFTB_CZ") ? atoll(getenv("OFFTB_CZ")) : 0;   // experiments
   long long cz = env_cz > 0 ? env_cz : (E.prec == PREC_F64 ? 4 : 8);
+  if (E.narrow_now) cz /= 2;   // the chunk is what one CTA writes as a run: keep it equal to the tile's columns
   while (cz > 1 && myT % cz) cz /= 2;
   return cz;
 }
@@ -684,18 +691,37 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   auto tile_T = [&](int i) { return tile_Tk(0, i); };
   // fused exchange between processes: readers on the second stream, ordered against the writers by flags alone
   bool two = false;
+  E0.narrow_now = false;
   if (fused && !world().local && blocks > 1) {
     // shapes of tile 0's two launches, without launching
-    FftShape shw, shr;
-    Engine &E = E0;
-    E.grid_cap[0] = E.grid_cap[1] = 0;
-    E.dry_shape = &shw;
-    int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
-    E.dry_shape = &shr;
-    if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
-    E.dry_shape = nullptr;
-    if (rc) return -1;
-    two = plan_overlap(E, shw, shr);
+    auto try_overlap = [&]() -> int {
+      FftShape shw, shr;
+      Engine &E = E0;
+      E.grid_cap[0] = E.grid_cap[1] = 0;
+      E.dry_shape = &shw;
+      int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+      E.dry_shape = &shr;
+      if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+      E.dry_shape = nullptr;
+      if (rc) return -1;
+      return plan_overlap(E, shw, shr) ? 1 : 0;
+    };
+    int ov = try_overlap();
+    if (ov < 0) return -1;
+    // Long strided transforms (2048 points: 131 KB and the whole register file per CTA at 64 bytes per index) leave no
+    // room for a second kernel on the SM, and the exchange-bound writer would then run before the HBM-bound reader
+    // instead of beside it.  Half-width tiles (32 bytes per index, half the threads, registers and shared memory) fit
+    // two per SM: each kernel alone is slower, the phase as a whole is faster because the two overlap.
+    // OFFTB_NARROW=0 keeps the full-width tiles on one stream.  The decision is a function of the plan and the device
+    // only, so every rank takes the same one (the slot layout - the z chunk - depends on it).
+    static const bool narrow_env = !(getenv("OFFTB_NARROW") && atoi(getenv("OFFTB_NARROW")) == 0);
+    if (ov == 0 && narrow_env && overlap_wanted()) {
+      E0.narrow_now = true;
+      ov = try_overlap();
+      if (ov < 0) return -1;
+      if (ov == 0) { E0.narrow_now = false; E0.grid_cap[0] = E0.grid_cap[1] = 0; }
+    }
+    two = ov > 0;
   } else {
     E0.grid_cap[0] = E0.grid_cap[1] = 0;
   }
@@ -769,6 +795,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     E0.chain_timing = false;
   }
   for (Engine *Ep : engs) Ep->pdl_next = 0;
+  E0.narrow_now = false;
   if (two) {
     OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
     OFFTB_CUDA(cudaStreamWaitEvent(sc, R0.recvd[0], 0));
