@@ -74,7 +74,11 @@ def _lines(out, prefixes):
     return [l.rstrip() for l in out.splitlines() if l.startswith(prefixes)]
 
 
-@pytest.mark.parametrize("p,flags", [(1, []), (1, ["-S", "1", "-T", "8"]), (4, ["-o", "-d", "4"]), (4, ["-d", "2", "-t", "4", "-w", "1"])])
+@pytest.mark.parametrize("p,flags", [(1, []), (1, ["-S", "1", "-T", "8"]), (4, ["-o", "-d", "4"]), (4, ["-d", "2", "-t", "4", "-w", "1"]),
+                                     (1, ["-R"]), (1, ["-R", "-S", "1"]),                       # real-to-complex (run-fft.c:53-55, 183)
+                                     (1, ["-N", "12", "-n", "10", "-L", "9"]),                  # lengths with odd factors
+                                     (1, ["-N", "24", "-n", "20", "-L", "18", "-R"]),
+                                     (2, ["-N", "15", "-n", "10", "-L", "9", "-d", "2", "-o", "-V", "3"])])   # uneven split, exact counts
 def test_same_stdout_as_the_reference_driver(p, flags):
     """same driver source, two libraries: the reference's own (CPU, shims) and this one (GPU).  Everything the driver
     prints except the timings must agree: echoed flags, default and final parameter lines, the M/m line, the -v values."""
@@ -85,7 +89,7 @@ def test_same_stdout_as_the_reference_driver(p, flags):
     if not REF_EXE.exists():
         pytest.skip("oracle/_ref/run-fft not built")
     N = 64
-    args = ["-N", str(N), "-n", str(N), "-L", str(N), "-r", "1", "-m", "1", "-v", "-a", "0", "-c"] + flags   # -c: is_notest
+    args = ["-N", str(N), "-n", str(N), "-L", str(N), "-r", "1", "-m", "1", "-v", "-a", "0", "-c"] + flags   # -c: is_notest; later -N/-n/-L win
     import os
     ref = subprocess.run([str(REF_EXE)] + args, capture_output=True, text=True, timeout=300, env=dict(os.environ, OFFT_SHIM_NP=str(p)))
     cmd = [str(EXE)] + args if p == 1 else [str(ROOT / "offt_b200" / "bin" / "offtrun"), "-n", str(p), str(EXE)] + args

@@ -31,3 +31,16 @@ def test_nccl_ranks_match_oracle(mode):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     print(res.stdout[-4000:], res.stderr[-2000:])
     assert res.returncode == 0 and "MGPU PARITY PASSED" in res.stdout
+
+
+def test_lost_peer_times_out_with_a_message_and_the_context_survives():
+    """a flag wait must neither hang nor trap - the execute fails with a message, the next plan works"""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", str(ROOT / "tests" / "mgpu_timeout_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OFFTB_FLAG_TIMEOUT_S="3"))
+    print(res.stdout[-2000:], res.stderr[-2000:])
+    assert res.returncode == 0 and "MGPU TIMEOUT PASSED" in res.stdout
