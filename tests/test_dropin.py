@@ -100,3 +100,22 @@ def test_same_stdout_as_the_reference_driver(p, flags):
     a, b = _printed(got.stdout), _printed(ref.stdout)
     assert len(a) == len(b) == 4
     np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-3)
+
+
+@pytest.mark.parametrize("p,flags", [(1, ["-l", "4", "-s", "3"]), (2, ["-l", "6", "-s", "0", "-o"]), (2, ["-l", "5", "-s", "2", "-O", "2", "-o"])])
+def test_run_fft_with_tuning(p, flags):
+    """-l N: offt_3d_init tunes before it returns (offt-compute.c:3437-3448): the driver allocates for the largest
+    decomposition (run-fft.c:269-292), reads the layout afterwards, and its -v values must still be the ramp's DFT"""
+    import torch
+    if torch.cuda.device_count() < p:
+        pytest.skip(f"needs {p} GPUs")
+    _need_exe()
+    N = 64
+    args = ["-N", str(N), "-n", str(N), "-L", str(N), "-r", "2", "-m", "1", "-v", "-a", "0", "-c"] + flags
+    cmd = [str(EXE)] + args if p == 1 else [str(ROOT / "offt_b200" / "bin" / "offtrun"), "-n", str(p), str(EXE)] + args
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "@ BEST" in res.stdout
+    got = _printed(res.stdout)
+    assert len(got) == 4, res.stdout[-2000:]
+    np.testing.assert_allclose(got, _want(N), rtol=1e-9, atol=1e-3)
