@@ -409,3 +409,32 @@ def test_timer_buckets_are_filled_by_default():
         assert all(t[k] > 0 for k in (ALL, FFTz, FFTy1, FFTy2, FFTx, INIT1, INIT2))
         for pl in plans:
             pl.fin()
+
+
+@pytest.mark.parametrize("S", [1, 0])
+def test_full_size_512_cubed_against_an_independent_fft(S):
+    """BASELINE configs[1] at its full size, element by element: 512^3 complex128 on one GPU against scipy's pocketfft
+    (numpy.fft.fftn where scipy is absent) on the same seeded grid, read through ostart/osize/ostride"""
+    torch = _torch()
+    import offt_b200 as ob
+    from offt_b200 import layout
+    try:
+        import scipy.fft
+        fftn = lambda a: scipy.fft.fftn(a, workers=-1)   # noqa: E731
+    except ImportError:
+        fftn = np.fft.fftn
+    n = 512
+    rng = np.random.default_rng(512)
+    grid = rng.uniform(-1, 1, (n, n, n)) + 1j * rng.uniform(-1, 1, (n, n, n))
+    with local_world(1):
+        plan = ob.Plan(n, n, n, is_notest=1, custom={P.P1: 1, P.S: S})
+        box = plan.box()
+        a = torch.from_numpy(layout.scatter_input(box, grid, plan.alloc_elems)).to("cuda")
+        plan.execute(a)
+        got = layout.gather_output([box], [a.cpu().numpy()], (n, n, n))
+        plan.fin()
+    want = fftn(grid)
+    del grid
+    num = np.linalg.norm((got - want).ravel())
+    den = np.linalg.norm(want.ravel())
+    assert num / den < 1e-12
