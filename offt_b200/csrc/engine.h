@@ -121,6 +121,7 @@ struct Engine {
   unsigned long long wait_timeout_ns = 0;  // OFFTB_FLAG_TIMEOUT_S (default 300 s; 0: wait for ever)
   bool failed = false;                     // an exchange timed out: the plan's flags are no longer consistent
   bool narrow_now = false;                 // the phase being enqueued uses half-width strided tiles (run_phase)
+  int reader_depth = 0, depth_next = 0;    // ring depth of the reader launches while they share the SMs with the writers (plan_overlap)
   int pdl_next = 0;                        // dependent-launch bits of the next launch (run_phase sets, produce/consume read)
   bool chain_timing = false;               // stage timing of a dependent-launch chain: one event pair per chain
   std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)

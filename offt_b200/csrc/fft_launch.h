@@ -20,7 +20,7 @@ int fft_twiddle_table(int N, int prec, long double *out);
 // what one launch occupies: resolved ring depth, grid, and the per-CTA resources
 struct FftShape {
   int threads = 0, regs = 0, depth = 0, occ = 0, sm_count = 0;
-  size_t smem = 0;
+  size_t smem = 0;   // dynamic shared memory of the launch = depth ring slots
   unsigned grid = 0;
 };
 

@@ -188,6 +188,7 @@ struct Launch {
   unsigned signal_value = 0;
   unsigned *done_counter = nullptr;
   int grid_cap = 0;
+  int depth = 0; // > 0: ring slots of the launch (0: the launcher decides)
   int r2c = 0;   // z pass of a real-to-complex plan
   int pdl = 0;   // bit 0: let the next launch of the stream start early; bit 1: this launch may itself start early
 };
@@ -291,6 +292,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
     return 0;
   }
   a.pdl = L.pdl;
+  a.depth = L.depth;
   a.c_log = pick_c_log(E, info, L);
   a.bulk_store = bulk_store_ok(E, a, L.N) ? 1 : 0;
   if (a.ry_level >= 0 && a.load_cfast != a.store_cfast) { set_error("internal: Ry rule on a transposing launch"); return -1; }
@@ -559,6 +561,23 @@ bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
   long long gw = std::max<long long>(1, std::min<long long>(slots - 1, slots * std::min(std::max(share, 1), 99) / 100));
   E.grid_cap[0] = (int)gw;
   E.grid_cap[1] = (int)(slots - gw);
+  // Side by side each kernel holds about half the CTAs it would hold alone, and the reader - HBM-bound, long strided
+  // tiles, a one-slot ring when it sizes itself for an SM of its own - becomes the longer of the two chains (1024^3:
+  // 8.5 ms against 7.9 on 2 GPUs, 5.3 against 4.9 on 4).  The shared memory its missing twin CTAs would have taken is
+  // free, so its ring can be deepened as far as the SM's shared memory allows next to the writer's CTAs
+  // (OFFTB_READER_DEPTH=2 or 3).  Off by default: measured on 2 GPUs it shortens the reader chain by 5 % and the
+  // transform by under 1 % (11.11 -> 11.01 ms, profiles/r02_exchange_ab.md) - the phase is paced by the writer.
+  E.reader_depth = 0;
+  static const int env_rd = getenv("OFFTB_READER_DEPTH") ? atoi(getenv("OFFTB_READER_DEPTH")) : 0;
+  if (env_rd > 0 && r.depth > 0 && r.depth < 3) {
+    const size_t reserve = 1024 + 256;
+    const long long nw = (gw + w.sm_count - 1) / w.sm_count, nr = (slots - gw + w.sm_count - 1) / w.sm_count;
+    const size_t rslot = r.smem / (size_t)r.depth;
+    for (int d = env_rd > 0 ? env_rd : 3; d > r.depth; --d) {
+      if (rslot * d + reserve > (size_t)smem_sm) continue;
+      if ((size_t)nw * (w.smem + reserve) + (size_t)nr * (rslot * d + reserve) <= (size_t)smem_sm) { E.reader_depth = d; break; }
+    }
+  }
   return true;
 }
 
@@ -650,6 +669,7 @@ int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 2; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
   if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
   L.pdl = E.pdl_next;
+  L.depth = E.depth_next;
   return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
 }
 
@@ -663,6 +683,7 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
   if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
   L.pdl = E.pdl_next;
+  L.depth = E.depth_next;
   return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
 }
 
@@ -748,6 +769,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     Engine &E = *engs[k];
     if (tile_Tk(k, i) <= 0) return 0;
     E.pdl_next = pdl ? (1 | (n_first ? 2 : 0)) : 0;
+    E.depth_next = 0;
     if (E.chain_timing && !n_first) cudaEventRecord(ce[0], sc);
     ++n_first;
     return inverse ? consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, sc) : produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, sc);
@@ -756,6 +778,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     Engine &E = *engs[k];
     if (tile_Tk(k, i) <= 0) return 0;
     E.pdl_next = pdl ? (1 | (n_second ? 2 : 0)) : 0;
+    E.depth_next = two ? E.reader_depth : 0;
     if (E.chain_timing && !n_second) cudaEventRecord(ce[2], s2);
     ++n_second;
     return inverse ? produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, s2) : consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, s2);
@@ -794,7 +817,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     E0.timed.push_back({st_second, {ce[2], ce[3]}});
     E0.chain_timing = false;
   }
-  for (Engine *Ep : engs) Ep->pdl_next = 0;
+  for (Engine *Ep : engs) { Ep->pdl_next = 0; Ep->depth_next = 0; }
   E0.narrow_now = false;
   if (two) {
     OFFTB_CUDA(cudaEventRecord(R0.recvd[0], s2));
