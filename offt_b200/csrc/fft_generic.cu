@@ -31,6 +31,8 @@ __device__ __forceinline__ void split_n(const FftMap &m, int n, int &blk, int &l
   }
 }
 
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv &f) { return (__umulhi(n, f.m) + n) >> f.s; }
+
 template <typename T>
 __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant__ GenArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -39,7 +41,13 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
   const int tid = threadIdx.x, nthreads = blockDim.x;
   cx<T> *buf0 = reinterpret_cast<cx<T> *>(smem_raw);
   cx<T> *buf1 = buf0 + (size_t)C * N;
+  // the twiddle table sits behind the two buffers when it fits (every multiply-add of every stage gathers from it)
   const cx<T> *tw = (const cx<T> *)a.tw;
+  if (g.tw_in_smem) {
+    cx<T> *stw = buf1 + (size_t)C * N;
+    for (int k = tid; k < N; k += nthreads) stw[k] = tw[k];
+    tw = stw;
+  }
   const T cj = a.conj ? (T)-1 : (T)1;
 
   __shared__ void *s_tab[OFFTB_MAX_GROUP];
@@ -57,7 +65,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     if (a.real_mode == 1) {
       // rows of N real numbers in the in-place r2c layout: real n of the row that starts at complex offset o is double 2*o + n
       for (int e = tid; e < total; e += nthreads) {
-        const int n = e % N, c = e / N;
+        const int c = (int)fdiv((unsigned)e, g.dN), n = e - c * N;
         const T re = ((const T *)a.in)[2 * map_b(a.im, (unsigned)(b0 + c)) + n];
         buf0[c * N + n] = cx<T>{re, (T)0};
       }
@@ -65,7 +73,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
       // N/2+1 complex points per row, completed to the Hermitian row X[N-n] = conj(X[n])
       for (int e = tid; e < ncol * Nh; e += nthreads) {
         int c, n;
-        if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { n = e % Nh; c = e / Nh; }
+        if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { c = (int)fdiv((unsigned)e, g.dNh); n = e - c * Nh; }
         int blk, lo;
         split_n(a.im, n, blk, lo);
         cx<T> v = ((const cx<T> *)a.in)[map_b(a.im, (unsigned)(b0 + c)) + (long long)blk * a.im.n_hi + (long long)lo * a.im.n_lo];
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     } else {
       for (int e = tid; e < total; e += nthreads) {
         int c, n;
-        if (a.load_cfast) { c = e % ncol; n = e / ncol; } else { n = e % N; c = e / N; }
+        if (a.load_cfast) { n = ncol == C ? (int)fdiv((unsigned)e, g.dC) : e / ncol; c = e - n * ncol; } else { c = (int)fdiv((unsigned)e, g.dN); n = e - c * N; }
         int blk, lo;
         split_n(a.im, n, blk, lo);
         cx<T> v = ((const cx<T> *)a.in)[map_b(a.im, (unsigned)(b0 + c)) + (long long)blk * a.im.n_hi + (long long)lo * a.im.n_lo];
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
       const int R = g.radix[s];
       const int NR = N / R, step = N / (Ns * R);
       for (int e = tid; e < total; e += nthreads) {
-        const int c = e / N, o = e - c * N;
+        const int c = (int)fdiv((unsigned)e, g.dN), o = e - c * N;
         // Ry rule (offt-compute.c:1484, 1708): columns outside the window are moved, not transformed
         bool transform = true;
         if (a.ry_level >= 0) {
@@ -100,7 +108,8 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
           transform = a.ry_lo <= r && r < a.ry_hi;
         }
         if (!transform) { dst[e] = src[e]; continue; }
-        const int k = o % Ns, t = (o / Ns) % R, jhi = o / (Ns * R);
+        const int oq = (int)fdiv((unsigned)o, g.dNs[s]), k = o - oq * Ns;            // o = (jhi*R + t)*Ns + k
+        const int jhi = (int)fdiv((unsigned)oq, g.dR[s]), t = oq - jhi * R;
         const cx<T> *x = src + c * N + jhi * Ns + k;
         const int twb = (k + t * Ns) * step;   // < N
         cx<T> acc = x[0];
@@ -119,14 +128,15 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     // ---- store
     if (a.real_mode == 2) {
       for (int e = tid; e < total; e += nthreads) {
-        const int n = e % N, c = e / N;
+        const int c = (int)fdiv((unsigned)e, g.dN), n = e - c * N;
         ((T *)s_tab[0])[2 * map_b(a.om, (unsigned)(b0 + c)) + n] = src[c * N + n].x;
       }
     } else {
       const int Nst = a.real_mode == 1 ? Nh : N;   // a real row's spectrum is stored up to the Nyquist point only
       for (int e = tid; e < ncol * Nst; e += nthreads) {
         int c, n;
-        if (a.store_cfast) { c = e % ncol; n = e / ncol; } else { n = e % Nst; c = e / Nst; }
+        if (a.store_cfast) { n = ncol == C ? (int)fdiv((unsigned)e, g.dC) : e / ncol; c = e - n * ncol; }
+        else { c = (int)fdiv((unsigned)e, a.real_mode == 1 ? g.dNh : g.dN); n = e - c * Nst; }
         int blk, lo;
         split_n(a.om, n, blk, lo);
         cx<T> v = src[c * N + n];
@@ -197,7 +207,13 @@ cudaError_t fft_generic_launch(int N, int prec, const FftArgs &args, long long n
   cols = std::min<long long>(cols, std::max<long long>(nbatch, 1));
   if (2 * (size_t)cols * N * esz > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
   g.cols = (int)cols;
-  const size_t smem = 2 * (size_t)cols * N * esz;
+  g.dN = fastdiv_make((unsigned)N); g.dNh = fastdiv_make((unsigned)(N / 2 + 1)); g.dC = fastdiv_make((unsigned)cols);
+  for (int s = 0, Ns = 1; s < g.ns; ++s) {
+    g.dNs[s] = fastdiv_make((unsigned)Ns); g.dR[s] = fastdiv_make((unsigned)g.radix[s]); g.dNsR[s] = fastdiv_make((unsigned)(Ns * g.radix[s]));
+    Ns *= g.radix[s];
+  }
+  g.tw_in_smem = (2 * (size_t)cols + 1) * N * esz <= (size_t)smem_optin ? 1 : 0;
+  const size_t smem = (2 * (size_t)cols + (g.tw_in_smem ? 1 : 0)) * N * esz;
   const long long ntiles = (nbatch + cols - 1) / cols;
   int occ = 0;
   cudaError_t e = prec == PREC_F64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_generic_kernel<double>, 256, smem)

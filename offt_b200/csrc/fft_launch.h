@@ -39,9 +39,25 @@ cudaError_t fft_shape(int N, int prec, const FftArgs &args, long long nbatch, Ff
 
 // ---- any length, general block split (fft_generic.cu) ---------------------------------------------------------
 #define OFFTB_GEN_MAX_STAGES 24
+// n / d for n < 2^31 by one multiply-high and a shift (d fixed per launch; the generic kernel divides every element
+// index of every stage by the same few numbers)
+struct FastDiv {
+  unsigned m, s, d;
+};
+inline FastDiv fastdiv_make(unsigned d) {
+  FastDiv f;
+  f.d = d;
+  unsigned s = 0;
+  while ((1ULL << s) < d) ++s;
+  f.s = s;
+  f.m = (unsigned)(((1ULL << 32) * ((1ULL << s) - d)) / d + 1);
+  return f;
+}
 struct GenArgs {
   FftArgs a;          // maps (with the general split), peer table, flags; a.tw = full table exp(-2*pi*i*k/N), k < N
   int N, ns, cols;    // length, Stockham stages, columns per CTA
+  int tw_in_smem;     // the table is copied behind the two buffers at kernel start
+  FastDiv dN, dNh, dC, dNs[OFFTB_GEN_MAX_STAGES], dNsR[OFFTB_GEN_MAX_STAGES], dR[OFFTB_GEN_MAX_STAGES];   // divisors N, N/2+1, columns per CTA; Ns, Ns*R, R per stage
   int radix[OFFTB_GEN_MAX_STAGES];
   long long nbatch;
 };
