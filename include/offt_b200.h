@@ -110,6 +110,9 @@ int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int
  * only tile sizes, windows and _Ry_ move and istride / ostride stay what they were.  Trials run on an internal zeroed
  * device array. */
 int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1);
+/* the same loop with the reference's Active Harmony server proposing the points (strategy 0 nm.so, 1 pro.so, 2 random.so,
+ * 3 brute.so) where offt_b200/ah/_root was built, the built-in sources otherwise; what ah_tuning / `run-fft -l` use */
+int offtb_tune_harmony(struct _offt_plan *po, int max_loop, int verbose, int strategy, int search_p1);
 /* offt-tuning.c:426-737: writes the 25 starting vertices (grid indices) of the Nelder-Mead search to po->user_vertex_file */
 void write_initial_simplex(struct _offt_plan *po, int **v_list, int *v_list_size);
 

@@ -101,6 +101,7 @@ def _load():
     L.offtb_check_supported.argtypes = [i] * 5
     L.offtb_tune.argtypes = [C.POINTER(OfftPlan), vp, vp, i, i]
     L.offtb_tune_ex.argtypes = [C.POINTER(OfftPlan), vp, vp, i, i, i, i]
+    L.offtb_tune_harmony.argtypes = [C.POINTER(OfftPlan), i, i, i, i]
     L.offtb_set_exit_on_error(0)   # Python raises instead of exit(-1)
     return L
 
@@ -246,6 +247,14 @@ class Plan:
         n = lib.offtb_tune_ex(self.po, None, None, max_loop, verbose, strategy, int(search_p1))
         if n < 0:
             raise OfftError(f"offtb_tune_ex: {_err()}")
+        return n
+
+    def tune_harmony(self, max_loop=20, strategy=0, search_p1=False, verbose=0) -> int:
+        """the same loop with the reference's Active Harmony server proposing the points where its back end was built
+        (offt_b200/ah/_root), the built-in sources otherwise - what `run-fft -l` goes through"""
+        n = lib.offtb_tune_harmony(self.po, max_loop, verbose, strategy, int(search_p1))
+        if n < 0:
+            raise OfftError(f"offtb_tune_harmony: {_err()}")
         return n
 
     @property

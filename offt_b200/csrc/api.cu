@@ -318,13 +318,15 @@ double offtb_fft_rows(void *data, int n, long long stride, long long dist, long 
 }
 
 // ---- tuning --------------------------------------------------------------------------------------
-// ah_tuning (offt-tuning.c:744-1022) as offt_3d_init calls it (offt-compute.c:3440): the search of tune.cu with the
-// strategy the caller chose (-s: 0 Nelder-Mead, 1 PRO -> Nelder-Mead, 2 random, 3 brute -> coordinate descent), over
-// all decompositions (the caller lays out its array only after init returns, run-fft.c:269-304, 314)
-int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1);
+// ah_tuning (offt-tuning.c:744-1022) as offt_3d_init calls it (offt-compute.c:3440): the loop of tune.cu with the
+// strategy the caller chose (-s: 0 nm, 1 pro, 2 random, 3 brute) - through the reference's own Active Harmony server
+// where its back end was built (offt_b200/ah), through the built-in sources otherwise - over all decompositions (the
+// caller lays out its array only after init returns, run-fft.c:269-304, 314)
+int offtb_tune_harmony(struct _offt_plan *po, int max_loop, int verbose, int strategy, int search_p1);
 
 int ah_tuning(struct _offt_plan *po, double *in, double *out) {
-  return offtb_tune_ex(po, in, out, po->max_loop, !po->rank, po->ah_strategy, 1);
+  (void)in; (void)out;
+  return offtb_tune_harmony(po, po->max_loop, !po->rank, po->ah_strategy, 1);
 }
 
 }  // extern "C"

@@ -6,8 +6,15 @@
 // install the best point (:995-1006).  Infeasible points and database hits cost no measurement and do not count
 // against max_loop; ten times max_loop fetches end the search regardless (:893).
 //
-// What proposes the candidates - in the reference an Active Harmony server with its strategy plug-ins, reached over
-// TCP - is built in (SURVEY.md section 8 keeps the server out of scope):
+// What proposes the candidates:
+//   * Active Harmony itself, as in the reference, where its back end exists: offt_b200/ah/Makefile compiles the
+//     reference's UNMODIFIED hserver, session-core, strategy plug-ins (the patched nm.so included) and client library
+//     out of tree, and rank 0 drives a session exactly as ah_tuning does - 24 integer variables V00..V23 over grid
+//     indices, the strategy of -s, the initial simplex through SHSONG_USER_VERTEX_FILE, a server launched on localhost
+//     if none answers, fetch / report until max_loop or convergence, then the best point (search_active_harmony below,
+//     offt_b200/ah/ah_glue.c; offt-tuning.c:773-854, 893-913, 988-1019).  OFFTB_TUNER=builtin skips it, OFFTB_TUNER=ah
+//     insists on it.
+//   * otherwise (no reference tree at build time, no TCP, ...) the built-in sources of the same shape:
 //   strategy 0 / 1  Nelder-Mead over all 24 index coordinates, started from the reference's own initial simplex
 //                   (write_initial_simplex, offt-tuning.c:426-737; its patched nm.so does the same, strategies/nm.c:369-396)
 //   strategy 2      uniformly random grid points (random.so)
@@ -19,12 +26,16 @@
 // Tunables that do nothing on a GPU - the CPU cache sub-tile sizes and the MPI_Test frequencies - stay in the point
 // (the reference's space has 24 coordinates) but are pulled into range before the feasibility test and left out of the
 // database key, so that points differing only in them are measured once.
+#include <dlfcn.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "engine.h"
@@ -298,6 +309,122 @@ void search_coordinate(Search &S) {
   }
 }
 
+// ---- Active Harmony: the reference's own search server ---------------------------------------------------------------
+struct AhApi {
+  void *handle = nullptr;
+  std::string root;
+  int (*open)(const char *, int, const int *, int, const char *, int) = nullptr;
+  int (*fetch)(long *) = nullptr;
+  int (*report)(double) = nullptr;
+  int (*converged)() = nullptr;
+  int (*best)(long *) = nullptr;
+  void (*close)() = nullptr;
+  const char *(*error)() = nullptr;
+};
+
+// <dir of libofft_b200.so>/../ah/_root, or OFFTB_AH_ROOT
+bool ah_load(AhApi &A) {
+  std::string root;
+  if (const char *e = getenv("OFFTB_AH_ROOT")) root = e;
+  else {
+    Dl_info info;
+    if (!dladdr((void *)&ah_load, &info) || !info.dli_fname) return false;
+    std::string lib = info.dli_fname;
+    const size_t slash = lib.rfind('/');
+    root = (slash == std::string::npos ? std::string(".") : lib.substr(0, slash)) + "/../ah/_root";
+  }
+  const std::string so = root + "/lib/libofft_ah.so";
+  if (access(so.c_str(), R_OK) != 0) return false;
+  A.handle = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!A.handle) return false;
+  A.root = root;
+  A.open = (int (*)(const char *, int, const int *, int, const char *, int))dlsym(A.handle, "offtb_ah_open");
+  A.fetch = (int (*)(long *))dlsym(A.handle, "offtb_ah_fetch");
+  A.report = (int (*)(double))dlsym(A.handle, "offtb_ah_report");
+  A.converged = (int (*)())dlsym(A.handle, "offtb_ah_converged");
+  A.best = (int (*)(long *))dlsym(A.handle, "offtb_ah_best");
+  A.close = (void (*)())dlsym(A.handle, "offtb_ah_close");
+  A.error = (const char *(*)())dlsym(A.handle, "offtb_ah_error");
+  return A.open && A.fetch && A.report && A.converged && A.best && A.close && A.error;
+}
+
+// rank 0's integers to every rank (the reference's MPI_Bcast of the point, offt-tuning.c:920): a sum in which the
+// other ranks contribute zeros
+void bcast_ints(int *v, int n) {
+  World &w = world();
+  if (!w.nccl) return;
+  static int *d = nullptr;
+  static int cap = 0;
+  if (cap < n) { if (d) cudaFree(d); cudaMalloc(&d, sizeof(int) * n); cap = n; }
+  std::vector<int> h(v, v + n);
+  if (w.rank != 0) std::fill(h.begin(), h.end(), 0);
+  cudaMemcpy(d, h.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
+  nccl_api()->AllReduce(d, d, n, ncclInt, ncclSum, w.nccl, 0);
+  cudaMemcpy(v, d, sizeof(int) * n, cudaMemcpyDeviceToHost);
+}
+
+// Returns false if the server could not be reached on rank 0 (every rank learns it), so that the caller falls back.
+bool search_active_harmony(Search &S, int strategy) {
+  World &w = world();
+  const bool lead = w.rank == 0;
+  AhApi A;
+  int ok = 0;
+  char vertex_file[64] = "";
+  if (lead && ah_load(A)) {
+    std::vector<int> sizes(PARAM_COUNT);
+    std::vector<int *> v_list(PARAM_COUNT);
+    for (int i = 0; i < PARAM_COUNT; ++i) { sizes[i] = (int)S.grid[i].size(); v_list[i] = S.grid[i].data(); }
+    const char *vf = nullptr;
+    if (strategy == 0 || strategy == 1) {   // only nm and pro take the user simplex (offt-tuning.c:795-796)
+      int x0[PARAM_COUNT + 1][PARAM_COUNT];
+      srand(20161);
+      initial_simplex(S.Nx, S.Ny, S.Nz, S.p, S.po->is_oned, S.po->is_W0, S.po->is_notest, S.search_p1 ? S.po->tuning_mode : 0, v_list.data(), sizes.data(), x0);
+      snprintf(vertex_file, sizeof(vertex_file), "/tmp/offtb-uv-%d", (int)getpid());
+      if (FILE *f = fopen(vertex_file, "w")) {
+        for (int i = 0; i < PARAM_COUNT + 1; ++i) {
+          // a decomposition that is not being searched stays where it is in every vertex
+          if (!S.search_p1) x0[i][_P1_] = S.index_of(std::vector<int>(S.po->params->v, S.po->params->v + PARAM_COUNT))[_P1_];
+          for (int j = 0; j < PARAM_COUNT; ++j) fprintf(f, "%d ", x0[i][j]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+        vf = vertex_file;
+      }
+    }
+    const int port = getenv("HARMONY_S_PORT") ? 0 : 20000 + (int)(getpid() % 20000);
+    if (A.open(A.root.c_str(), PARAM_COUNT, sizes.data(), strategy, vf, port) == 0) ok = 1;
+    else if (S.verbose) printf("Active Harmony not available (%s): using the built-in search\n", A.error());
+  }
+  bcast_ints(&ok, 1);
+  if (!ok) { if (lead && vertex_file[0]) remove(vertex_file); return false; }
+  if (lead && S.verbose) printf("Starting Harmony...\n");
+  while (true) {
+    int msg[1 + PARAM_COUNT] = {0};   // [0]: 1 = converged / out of budget
+    if (lead) {
+      if (!S.budget_left() || A.converged() == 1) msg[0] = 1;
+      else {
+        long idx[PARAM_COUNT];
+        if (A.fetch(idx) < 0) msg[0] = 1;
+        for (int i = 0; i < PARAM_COUNT; ++i) msg[1 + i] = (int)idx[i];
+      }
+    }
+    bcast_ints(msg, 1 + PARAM_COUNT);
+    if (msg[0]) break;
+    const double perf = S.evaluate(S.values_of(std::vector<int>(msg + 1, msg + 1 + PARAM_COUNT)));
+    if (lead) A.report(perf);
+  }
+  if (lead) {
+    long idx[PARAM_COUNT];
+    if (S.verbose && A.best(idx) >= 0) {
+      std::vector<int> b = S.values_of(std::vector<int>(idx, idx + PARAM_COUNT));
+      printf("@ HARMONY BEST "); print_params(b.data());
+    }
+    A.close();
+    if (vertex_file[0]) remove(vertex_file);
+  }
+  return true;
+}
+
 }  // namespace
 
 }  // namespace offtb
@@ -308,10 +435,9 @@ using namespace offtb;
 // comment); search_p1: also search what changes the caller's layout - the decomposition P1 and the output order S
 // (the caller must not have read po->comm yet, as in the reference where tuning happens inside offt_3d_init).
 // Returns the number of points measured, or a negative code.
-extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1) {
+static int tune_impl(struct _offt_plan *po, int max_loop, int verbose, int strategy, int search_p1, int use_ah) {
   if (!po || !po->b200) { set_error("null plan"); return -1; }
   if (world().local && world().size > 1) { set_error("tuning runs one rank per process"); return -1; }
-  (void)in; (void)out;   // trials run on an internal zeroed device array (offt-tuning.c:958 zeroes the caller's)
   Search S;
   S.po = po;
   S.Nx = po->Nx; S.Ny = po->Ny; S.Nz = po->is_r2c ? po->Nz / 2 + 1 : po->Nz; S.p = po->p;   // offt-tuning.c:110, 161
@@ -326,10 +452,19 @@ extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int
   if (S.search_p1 && po->tuning_mode == 2) { S.search_p1 = false; S.fixed_p1 = po->p; }
   const std::vector<int> start(po->params->v, po->params->v + PARAM_COUNT);
   if (((Engine *)po->b200)->sched == SCHED_SINGLE && !S.search_p1) max_loop = S.max_loop = std::min(max_loop, 2);   // one rank: nothing to search but S
-  switch (strategy) {
-    case 0: case 1: search_nelder_mead(S); break;
-    case 2: search_random(S); break;
-    default: search_coordinate(S); break;
+  // the reference's own search server where its back end was built (strategies 0..3 = nm, pro, random, brute); the
+  // built-in sources otherwise.  Strategy 3 maps to the built-in coordinate descent unless Active Harmony is asked for.
+  const char *tuner = getenv("OFFTB_TUNER");
+  const bool want_ah = tuner ? strcmp(tuner, "ah") == 0 : (use_ah != 0 && strategy != 3);
+  bool done = false;
+  if (want_ah && world().up && !(world().local && world().size > 1)) done = search_active_harmony(S, strategy);
+  if (!done && tuner && strcmp(tuner, "ah") == 0) { set_error("OFFTB_TUNER=ah: the Active Harmony back end is not available (offt_b200/ah/_root)"); return -1; }
+  if (!done) {
+    switch (strategy) {
+      case 0: case 1: search_nelder_mead(S); break;
+      case 2: search_random(S); break;
+      default: search_coordinate(S); break;
+    }
   }
   if (S.best_v.empty()) {
     // nothing feasible was measured: put the plan back where it started
@@ -342,6 +477,17 @@ extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int
   po->params->is_converged = 1;
   if (verbose) { printf("@ BEST "); print_params(po->params->v); printf("@ BEST %.5f\n", S.best_t); }
   return S.measured;
+}
+
+// trials run on an internal zeroed device array (offt-tuning.c:958 zeroes the caller's), so in / out are not touched
+extern "C" int offtb_tune_ex(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose, int strategy, int search_p1) {
+  (void)in; (void)out;
+  return tune_impl(po, max_loop, verbose, strategy, search_p1, 0);
+}
+
+// what ah_tuning calls: like offtb_tune_ex, with the Active Harmony server as the candidate source where available
+extern "C" int offtb_tune_harmony(struct _offt_plan *po, int max_loop, int verbose, int strategy, int search_p1) {
+  return tune_impl(po, max_loop, verbose, strategy, search_p1, 1);
 }
 
 extern "C" int offtb_tune(struct _offt_plan *po, double *in, double *out, int max_loop, int verbose) {

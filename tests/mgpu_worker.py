@@ -133,6 +133,32 @@ def main():
         failures += 0 if ok else 1
         print(f"{'ok  ' if ok else 'FAIL'} tuning incl. P1 (Nelder-Mead): {trials} trials -> P1 {tuned[P.P1]} T1 {tuned[P.T1]} W1 {tuned[P.W1]} T2 {tuned[P.T2]} W2 {tuned[P.W2]} S {tuned[P.S]}, "
               f"same on all ranks {same}, vs numpy {e:.2e}", flush=True)
+    # and through the reference's own Active Harmony server (hserver + patched nm.so, built unmodified by offt_b200/ah)
+    # where that back end travelled with the repo; elsewhere the same call falls back to the built-in Nelder-Mead
+    N, oned = (64, 64, 128), 0
+    grid = O.grid_values(8, *N)
+    plan = ob.Plan(*N, is_oned=oned, is_notest=1, custom={P.P1: world})
+    ah_built = (ROOT / "offt_b200" / "ah" / "_root" / "lib" / "libofft_ah.so").exists()
+    trials = plan.tune_harmony(8, strategy=0, search_p1=True, verbose=int(rank == 0))
+    tuned = plan.params
+    box = box_of(plan, N, world)
+    arr = torch.from_numpy(np.ascontiguousarray(O.scatter_input(box, grid))).to(dev)
+    plan.execute(arr)
+    fwd = arr.cpu().numpy()
+    plan.fin()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (box, fwd, tuned))
+    if rank == 0:
+        boxes = []
+        for b, f, _ in gathered:
+            b.data = f
+            boxes.append(b)
+        same = all(g[2] == tuned for g in gathered)
+        e = O.rel_l2(O.gather_output(boxes), np.fft.fftn(grid))
+        ok = same and e < 1e-12 and trials >= 1
+        failures += 0 if ok else 1
+        print(f"{'ok  ' if ok else 'FAIL'} tuning through Active Harmony ({'hserver + nm.so' if ah_built else 'back end not built: built-in fallback'}): {trials} trials -> "
+              f"P1 {tuned[P.P1]} T1 {tuned[P.T1]} W1 {tuned[P.W1]} T2 {tuned[P.T2]} W2 {tuned[P.W2]} S {tuned[P.S]}, same on all ranks {same}, vs numpy {e:.2e}", flush=True)
     ob.world_fin()
     ft = torch.tensor([failures], device=dev)
     dist.broadcast(ft, 0)

@@ -116,6 +116,8 @@ def test_run_fft_with_tuning(p, flags):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "@ BEST" in res.stdout
+    if (ROOT / "offt_b200" / "ah" / "_root" / "lib" / "libofft_ah.so").exists() and "-s" in flags and flags[flags.index("-s") + 1] in ("0", "2"):
+        assert "Starting Harmony..." in res.stdout    # the reference's own server proposed the points (offt-tuning.c:838)
     got = _printed(res.stdout)
     assert len(got) == 4, res.stdout[-2000:]
     np.testing.assert_allclose(got, _want(N), rtol=1e-9, atol=1e-3)
