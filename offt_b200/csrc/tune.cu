@@ -121,14 +121,25 @@ struct Search {
     return engine_create(po) == 0;
   }
 
-  // one point: repaired, tested, looked up, measured.  Returns its time in seconds (kInfeasible if it cannot run).
-  double evaluate(std::vector<int> v) {
-    ++fetched;
+  // what a candidate becomes before it is tested: pinned layout knobs, ADJUST_POINT, the dead knobs pulled into range
+  std::vector<int> repaired(std::vector<int> v) const {
     if (!search_p1) v[_P1_] = fixed_p1;
     if (!search_layout) v[_S_] = fixed_S;   // the caller has read the output strides already
     params_adjust(Nx, Ny, Nz, p, po->is_oned, v.data());
     repair_ignored(Nx, Ny, Nz, p, v.data());
     if (po->is_W0) v[_W1_] = v[_W2_] = 0;
+    return v;
+  }
+  static std::vector<int> key_of(const std::vector<int> &v) {
+    std::vector<int> key;
+    for (int k : kLive) key.push_back(v[k]);
+    return key;
+  }
+
+  // one point: repaired, tested, looked up, measured.  Returns its time in seconds (kInfeasible if it cannot run).
+  double evaluate(std::vector<int> v) {
+    ++fetched;
+    v = repaired(v);
     int bad;
     // the ring-size rule of the reference is about MPI_Alloc_mem on its clusters; HBM has room for far larger rings,
     // so only the structural rules decide here - and the memory actually free on the device (below)
@@ -140,8 +151,7 @@ struct Search {
     const int p1 = v[_P1_], p2 = p / p1;
     const long long M1 = cd(Nx, p1), M2 = cd(Ny, p2), M3 = cd(Nz, p2), M4 = cd(Ny, p1);
     if (v[_W1_] > cd((int)M1, v[_T1_]) || v[_W2_] > cd((int)M3, v[_T2_])) return kInfeasible;
-    std::vector<int> key;
-    for (int k : kLive) key.push_back(v[k]);
+    const std::vector<int> key = key_of(v);
     auto it = database.find(key);
     if (it != database.end()) {
       if (verbose) { printf("%.5f FOUND IN DATABASE ", it->second); print_params(v.data()); }
@@ -413,14 +423,21 @@ bool search_active_harmony(Search &S, int strategy) {
     const double perf = S.evaluate(S.values_of(std::vector<int>(msg + 1, msg + 1 + PARAM_COUNT)));
     if (lead) A.report(perf);
   }
+  // the server's best point (harmony_best, offt-tuning.c:995-1000) is installed if it was measured and is no slower
+  // than the best measurement this loop saw (the two differ only when equal keys or repaired points are involved)
+  int bmsg[1 + PARAM_COUNT] = {0};
   if (lead) {
     long idx[PARAM_COUNT];
-    if (S.verbose && A.best(idx) >= 0) {
-      std::vector<int> b = S.values_of(std::vector<int>(idx, idx + PARAM_COUNT));
-      printf("@ HARMONY BEST "); print_params(b.data());
-    }
+    if (A.best(idx) >= 0) { bmsg[0] = 1; for (int i = 0; i < PARAM_COUNT; ++i) bmsg[1 + i] = (int)idx[i]; }
     A.close();
     if (vertex_file[0]) remove(vertex_file);
+  }
+  bcast_ints(bmsg, 1 + PARAM_COUNT);
+  if (bmsg[0]) {
+    const std::vector<int> b = S.repaired(S.values_of(std::vector<int>(bmsg + 1, bmsg + 1 + PARAM_COUNT)));
+    auto it = S.database.find(Search::key_of(b));
+    if (lead && S.verbose) { printf("@ HARMONY BEST "); print_params(const_cast<int *>(b.data())); }
+    if (it != S.database.end() && it->second < kInfeasible && it->second <= S.best_t) { S.best_t = it->second; S.best_v = b; }
   }
   return true;
 }
