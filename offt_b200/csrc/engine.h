@@ -127,6 +127,8 @@ struct Engine {
   std::vector<void *> peer_ring;           // every world rank's ring chunk as mapped here (fused mode)
   std::vector<void *> peer_flags;          // every world rank's flag block as mapped here
   void *tw[3] = {nullptr, nullptr, nullptr};  // twiddles for Nx, Ny, Nz (compact per-stage tables of the power-of-two kernels)
+  void *tw_half = nullptr, *tw_r2c = nullptr;      // real-to-complex plans: tables of the Nz/2-point transform and exp(-2*pi*i*k/Nz), k <= Nz/4
+  bool r2c_fast = false;                           // the local z pass runs as Nz/2 complex points + r2c_pass.cu
   void *tw_full[3] = {nullptr, nullptr, nullptr};  // exp(-2*pi*i*k/N), k < N, for the generic kernel
   Ring ring[2];
   cudaStream_t s_comp = nullptr, s_comm = nullptr, s_user = nullptr;

@@ -70,4 +70,8 @@ int fft_generic_twiddle_table(int N, long double *out);
 // launches (or, with shape_only, only sizes) the generic kernel; nbatch may be 0 (the launch then only waits and signals)
 cudaError_t fft_generic_launch(int N, int prec, const FftArgs &args, long long nbatch, cudaStream_t stream, FftShape *shape_only);
 
+// ---- O(N) step between an H-point complex transform and the N = 2H point real one (r2c_pass.cu) -----------------------
+cudaError_t r2c_step_launch(int prec, bool backward, const void *in, void *out, const void *w, const FftMap &im, const FftMap &om, int H,
+                            long long nbatch, cudaStream_t stream);
+
 }  // namespace offtb

@@ -188,6 +188,7 @@ struct Launch {
   unsigned signal_value = 0;
   unsigned *done_counter = nullptr;
   int grid_cap = 0;
+  const void *tw = nullptr;   // twiddle table other than the axis' own (the half-length transform of a real z pass)
   int depth = 0; // > 0: ring slots of the launch (0: the launcher decides)
   int r2c = 0;   // z pass of a real-to-complex plan
   int pdl = 0;   // bit 0: let the next launch of the stream start early; bit 1: this launch may itself start early
@@ -255,6 +256,22 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
   FftKernelInfo info;
   const bool generic = g_force_generic > 0 || L.nbatch == 0 || L.r2c || L.im.gg > 0 || L.om.gg > 0 || !fft_kernel_info(L.N, E.prec, &info);
   if (L.nbatch >= (1LL << 32)) { set_error("batch of %lld rows exceeds the 32-bit batch index", L.nbatch); return -1; }
+  // Strided launches take their columns from the fastest batch digit, which must hold a whole number of tiles.  An
+  // extent that does not (the Nz/2+1 = 257 complex points of a real-to-complex row, an odd local share) would fall
+  // back to one column - 16-byte accesses - for the whole launch; instead the launch is split into the part that
+  // tiles at full width and the remainder.  Not for launches that take part in a flag protocol (one signal per tile).
+  if (!generic && !E.dry_shape && (L.load_cfast || L.store_cfast) && L.signal_count == 0 && L.wait_count == 0 && L.im.B0 == L.om.B0) {
+    const unsigned want = (unsigned)(64 / E.esz), B0 = L.im.B0;
+    if (B0 > want && B0 % want != 0) {
+      const unsigned main = B0 / want * want, rem = B0 - main;
+      Launch A = L, B = L;
+      A.im.B0 = A.om.B0 = main; A.nbatch = L.nbatch / B0 * main;
+      B.im.B0 = B.om.B0 = rem; B.nbatch = L.nbatch / B0 * rem;
+      B.im.off += (long long)main * L.im.s0; B.om.off += (long long)main * L.om.s0;
+      if (run_launch(E, st, stage, A, inverse)) return -1;
+      return run_launch(E, st, stage, B, inverse);
+    }
+  }
   FftArgs a;
   memset(&a, 0, sizeof(a));
   if (inverse) {
@@ -262,7 +279,7 @@ int run_launch(Engine &E, cudaStream_t st, int stage, Launch L, bool inverse) {
     std::swap(L.load_cfast, L.store_cfast);
     const void *t = L.in; L.in = L.out; L.out = const_cast<void *>(t);
   }
-  a.in = L.in; a.out = L.out; a.tw = generic ? E.tw_full[L.axis] : E.tw[L.axis];
+  a.in = L.in; a.out = L.out; a.tw = L.tw ? L.tw : generic ? E.tw_full[L.axis] : E.tw[L.axis];
   a.im = L.im; a.om = L.om;
   a.load_cfast = L.load_cfast; a.store_cfast = L.store_cfast;
   a.conj = inverse ? 1 : 0;
@@ -827,6 +844,36 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   return 0;
 }
 
+// Local z pass.  Complex plans: one launch.  Real-to-complex plans whose half length has a register-butterfly kernel:
+// the rows are transformed as Nz/2 complex points in place and r2c_pass.cu turns that spectrum into the Nz/2+1 points of
+// the real transform on the way to where the launch would have stored them (backward: the reverse).  Other real plans
+// (odd Nz, half lengths without a fast kernel) and the fused z pass of phase 1 run on the any-length kernel.
+int run_z_pass(Engine &E, cudaStream_t st, Launch L, bool inverse) {
+  if (!(L.r2c && E.r2c_fast)) return run_launch(E, st, ST_K1, L, inverse);
+  const int H = L.N / 2;
+  Launch Lh = L;
+  Lh.N = H; Lh.r2c = 0; Lh.tw = E.tw_half;
+  Lh.out = const_cast<void *>(L.in); Lh.om = L.im;     // in place in the caller's array, where the real rows live
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool timed = E.stage_timing && !E.async;
+  const bool was = E.stage_timing;
+  if (timed) { e0 = pool_event(E); e1 = pool_event(E); cudaEventRecord(e0, st); E.stage_timing = false; }   // one event pair for both kernels
+  int rc = 0;
+  cudaError_t ce = cudaSuccess;
+  if (!inverse) {
+    rc = run_launch(E, st, ST_K1, Lh, false);
+    if (!rc && !E.dry_shape) ce = r2c_step_launch(E.prec, false, L.in, L.out, E.tw_r2c, L.im, L.om, H, L.nbatch, st);
+  } else {
+    if (!E.dry_shape) ce = r2c_step_launch(E.prec, true, L.out, const_cast<void *>(L.in), E.tw_r2c, L.om, L.im, H, L.nbatch, st);
+    if (ce == cudaSuccess) rc = run_launch(E, st, ST_K1, Lh, true);
+  }
+  E.stage_timing = was;
+  if (ce != cudaSuccess) { set_error("r2c step (N=%d, batch=%lld): %s", L.N, L.nbatch, cudaGetErrorString(ce)); return -1; }
+  if (timed) { cudaEventRecord(e1, st); E.timed.push_back({ST_K1, {e0, e1}}); }
+  if (!rc && !E.dry_shape) E.launches++;
+  return rc;
+}
+
 int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inverse) {
   Engine &E0 = *engs[0];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp;
@@ -856,10 +903,10 @@ int run_schedule(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, bool inve
       Engine &E = *engs[k];
       const Dims d = dims_of(E.po);
       int rc = 0;
-      if (s == STEP_Z_SWAP) rc = run_launch(E, sc, ST_K1, L_fftz_swap(d, bufs[k].U, bufs[k].A), inverse);
+      if (s == STEP_Z_SWAP) rc = run_z_pass(E, sc, L_fftz_swap(d, bufs[k].U, bufs[k].A), inverse);
       else if (s == STEP_X_SWAP) rc = run_launch(E, sc, ST_K4, L_fftx_swap(d, bufs[k].A, bufs[k].U), inverse);
       else if (s == STEP_Y_OUT) rc = run_launch(E, sc, ST_K2, L_ffty_out(d, bufs[k].U), inverse);
-      else if (s == STEP_Z_LOCAL) rc = run_launch(E, sc, ST_K1, L_fftz_local(d, bufs[k].U, bufs[k].A, 0, d.m1), inverse);
+      else if (s == STEP_Z_LOCAL) rc = run_z_pass(E, sc, L_fftz_local(d, bufs[k].U, bufs[k].A, 0, d.m1), inverse);
       else if (s == STEP_Y_LOCAL) rc = run_launch(E, sc, ST_K2, L_ffty_local(d, bufs[k].A), inverse);
       else rc = run_launch(E, sc, ST_K4, L_fftx_local(d, bufs[k].A, bufs[k].U), inverse);
       if (rc) return -1;
@@ -903,6 +950,29 @@ int engine_create(struct _offt_plan *po) {
   const int Ns[3] = {po->Nx, po->Ny, po->Nz};
   for (int a = 0; a < 3; ++a)
     if (make_twiddles(Ns[a], E->prec, &E->tw[a]) || make_twiddles_full(Ns[a], E->prec, &E->tw_full[a])) return -1;
+  // real-to-complex plans: the local z pass runs as a half-length complex transform plus the O(N) step of r2c_pass.cu
+  // when that half length has a register-butterfly kernel (OFFTB_R2C_FAST=0: always the any-length kernel)
+  {
+    FftKernelInfo hinfo;
+    const bool env_on = !(getenv("OFFTB_R2C_FAST") && atoi(getenv("OFFTB_R2C_FAST")) == 0);
+    if (po->is_r2c && env_on && po->Nz % 2 == 0 && po->Nz >= 4 && fft_kernel_info(po->Nz / 2, E->prec, &hinfo)) {
+      const int H = po->Nz / 2;
+      if (make_twiddles(H, E->prec, &E->tw_half)) return -1;
+      const long double two_pi = 6.283185307179586476925286766559005768L;
+      const int cnt = H / 2 + 1;
+      std::vector<double> hd(2 * (size_t)cnt);
+      std::vector<float> hf(2 * (size_t)cnt);
+      for (int k = 0; k < cnt; ++k) {
+        const long double ang = two_pi * (long double)k / (long double)po->Nz;
+        hd[2 * k] = (double)cosl(ang); hd[2 * k + 1] = (double)-sinl(ang);
+        hf[2 * k] = (float)cosl(ang); hf[2 * k + 1] = (float)-sinl(ang);
+      }
+      const size_t bytes = (size_t)cnt * E->esz;
+      OFFTB_CUDA(cudaMalloc(&E->tw_r2c, bytes));
+      OFFTB_CUDA(cudaMemcpy(E->tw_r2c, E->prec == PREC_F64 ? (void *)hd.data() : (void *)hf.data(), bytes, cudaMemcpyHostToDevice));
+      E->r2c_fast = true;
+    }
+  }
   OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comp, cudaStreamNonBlocking));
   OFFTB_CUDA(cudaStreamCreateWithFlags(&E->s_comm, cudaStreamNonBlocking));
   OFFTB_CUDA(cudaEventCreate(&E->ev_begin));
@@ -1000,6 +1070,7 @@ void engine_destroy(struct _offt_plan *po) {
   if (E->h_error) cudaFreeHost(E->h_error);
   if (E->registered_host) cudaHostUnregister(E->registered_host);
   for (int a = 0; a < 3; ++a) { cudaFree(E->tw[a]); cudaFree(E->tw_full[a]); }
+  cudaFree(E->tw_half); cudaFree(E->tw_r2c);
   cudaFree(E->d_user); cudaFree(E->d_scratch); cudaFree(E->d_ring);
   free_ring(E->ring[0]); free_ring(E->ring[1]);
   for (cudaEvent_t e : E->event_pool) cudaEventDestroy(e);
