@@ -576,8 +576,25 @@ bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
   const long long slots = per_sm * w.sm_count;
   static const int share = getenv("OFFTB_WRITER_SHARE") ? atoi(getenv("OFFTB_WRITER_SHARE")) : 50;
   long long gw = std::max<long long>(1, std::min<long long>(slots - 1, slots * std::min(std::max(share, 1), 99) / 100));
+  // A writer whose CTAs are smaller than the places above (sized for the larger kernel: contiguous-row K1 beside a
+  // strided reader) may fill what the reader's share leaves of an SM with more of them: the exchange-bound kernel wants
+  // every store-issuing warp it can get.  Only the reader's cap is what keeps the SMs from filling with waiting CTAs;
+  // writers never wait for a later tile, so they drain whatever their number.  OFFTB_WRITER_PACK=0 keeps equal places.
+  static const bool pack = !(getenv("OFFTB_WRITER_PACK") && atoi(getenv("OFFTB_WRITER_PACK")) == 0);
+  const long long gr = slots - gw;
+  if (pack) {
+    const long long nr = (gr + w.sm_count - 1) / w.sm_count;   // readers per SM when they spread evenly
+    const int wregs = (w.regs + 7) / 8 * 8, rregs = (r.regs + 7) / 8 * 8;
+    const int wwarps = (w.threads + 31) / 32, rwarps = (r.threads + 31) / 32;
+    const size_t wsmem = w.smem + 1024 + 256, rsmem = r.smem + 1024 + 256;
+    const long long by_regs = ((long long)regs_sm - nr * rregs * 32LL * rwarps) / ((long long)wregs * 32 * wwarps);
+    const long long by_smem = ((long long)smem_sm - nr * (long long)rsmem) / (long long)wsmem;
+    const long long by_thr = ((long long)thr_sm - nr * r.threads) / w.threads;
+    const long long nw = std::min({by_regs, by_smem, by_thr, 32LL});
+    if (nw * w.sm_count > gw) gw = nw * w.sm_count;
+  }
   E.grid_cap[0] = (int)gw;
-  E.grid_cap[1] = (int)(slots - gw);
+  E.grid_cap[1] = (int)gr;
   // Side by side each kernel holds about half the CTAs it would hold alone, and the reader - HBM-bound, long strided
   // tiles, a one-slot ring when it sizes itself for an SM of its own - becomes the longer of the two chains (1024^3:
   // 8.5 ms against 7.9 on 2 GPUs, 5.3 against 4.9 on 4).  The shared memory its missing twin CTAs would have taken is
@@ -588,7 +605,7 @@ bool plan_overlap(Engine &E, const FftShape &w, const FftShape &r) {
   static const int env_rd = getenv("OFFTB_READER_DEPTH") ? atoi(getenv("OFFTB_READER_DEPTH")) : 0;
   if (env_rd > 0 && r.depth > 0 && r.depth < 3) {
     const size_t reserve = 1024 + 256;
-    const long long nw = (gw + w.sm_count - 1) / w.sm_count, nr = (slots - gw + w.sm_count - 1) / w.sm_count;
+    const long long nw = (gw + w.sm_count - 1) / w.sm_count, nr = (gr + w.sm_count - 1) / w.sm_count;
     const size_t rslot = r.smem / (size_t)r.depth;
     for (int d = env_rd > 0 ? env_rd : 3; d > r.depth; --d) {
       if (rslot * d + reserve > (size_t)smem_sm) continue;
