@@ -17,6 +17,16 @@ __global__ void k_stg(double2 *dst, size_t elems_per_cta_iter, int iters, size_t
   }
 }
 
+// the same sweep with 32 bytes per lane (st.global.v4.f64, sm_100+): does a wider store per thread change the NVLink packets?
+__global__ void k_stg32(double4 *dst, size_t elems_per_cta_iter, int iters, size_t total_elems) {
+  const double a = threadIdx.x, b = blockIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    size_t base = (((size_t)i * gridDim.x + blockIdx.x) * elems_per_cta_iter) % total_elems;
+    for (size_t e = threadIdx.x; e < elems_per_cta_iter; e += blockDim.x)
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + base + e), "d"(a), "d"(b), "d"(a), "d"(b) : "memory");
+  }
+}
+
 __global__ void k_bulk(char *dst, int chunk_bytes, int chunks_per_tile, int iters, size_t total_bytes, int max_groups) {
   extern __shared__ __align__(128) char sm[];
   for (int j = threadIdx.x; j < chunk_bytes * chunks_per_tile / 16; j += blockDim.x) ((double2 *)sm)[j] = make_double2(j, blockIdx.x);
@@ -75,6 +85,15 @@ int main() {
         const int iters = (int)(total / (8192ull * ctas));
         snprintf(name, sizeof(name), "stg  %d CTAs x %d thr, 8 KB chunks", ctas, threads);
         run(name, bidir, [&](int d) { k_stg<<<ctas, threads, 0, st[d]>>>((double2 *)buf[1 - d], chunk_elems, iters, bytes / 16); });
+      }
+    }
+    for (int ctas : {148, 296}) {
+      for (int threads : {256, 512}) {
+        char name[128];
+        const size_t chunk_elems = 8192 / 32;   // 8 KB per CTA iteration, 32 B per lane
+        const int iters = (int)(total / (8192ull * ctas));
+        snprintf(name, sizeof(name), "stg32 %d CTAs x %d thr, 8 KB chunks, 32 B per lane", ctas, threads);
+        run(name, bidir, [&](int d) { k_stg32<<<ctas, threads, 0, st[d]>>>((double4 *)buf[1 - d], chunk_elems, iters, bytes / 32); });
       }
     }
     for (int ctas : {148, 296}) {
