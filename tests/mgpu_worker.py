@@ -80,6 +80,34 @@ def main():
             failures += 0 if ok else 1
             print(f"{'ok  ' if ok else 'FAIL'} N={N} p={world} oned={oned} custom={custom} bits={bits}: vs oracle {e1:.2e}  vs numpy {e2:.2e}  "
                   f"round trip {e3:.2e}  launches/rank {launches}", flush=True)
+    # real-to-complex plans between real ranks: slabs take the half-length fast path for their local z pass, phase-1 z
+    # passes (slab 1 x p, pencils) the any-length kernel; forward vs numpy.fft.rfftn, backward returns N * the real input
+    ob.set_default_precision(64)
+    r2c_cases = [((64, 32, 128), 1, {P.P1: world}), ((32, 64, 250), 1, {P.P1: 1, P.S: 1})]
+    if world >= 4:
+        r2c_cases.append(((64, 64, 96), 0, {P.P1: 2, P.T1: 8, P.T2: 5}))
+    for N, oned, custom in r2c_cases:
+        grid = O.grid_values(13, *N)
+        plan = ob.Plan(*N, is_oned=oned, is_notest=1, is_r2c=1, custom=custom)
+        box = box_of(plan, N, world)
+        arr = torch.from_numpy(np.ascontiguousarray(O.scatter_input_r2c(box, np.ascontiguousarray(grid.real)))).to(dev)
+        plan.execute(arr)
+        fwd = arr.cpu().numpy()
+        plan.execute_inverse(arr)
+        back = arr.cpu().numpy()
+        plan.fin()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (box, fwd, back))
+        if rank == 0:
+            boxes = []
+            for b, f, _ in gathered:
+                b.data = f
+                boxes.append(b)
+            e1 = O.rel_l2(O.gather_output_r2c(boxes), np.fft.rfftn(grid.real))
+            e2 = O.rel_l2(O.gather_input_r2c(boxes, [g[2] for g in gathered]) / np.prod(N), grid.real)
+            ok = e1 < 1e-12 and e2 < 1e-12
+            failures += 0 if ok else 1
+            print(f"{'ok  ' if ok else 'FAIL'} r2c N={N} p={world} oned={oned} custom={custom}: vs numpy rfftn {e1:.2e}  round trip {e2:.2e}", flush=True)
     # the tuning loop (ah_tuning's fetch -> measure -> report, offt-tuning.c:879-1006) on the device: the plan must
     # come back with a feasible point on the reference's grid, identical on every rank, and still transform correctly
     ob.set_default_precision(64)
