@@ -692,30 +692,31 @@ int fuse_reader(Engine &E, Launch &L, int phase, int tile) {
 struct Bufs { void *U; void *A; };   // caller's array and the array between the phases (U or scratch)
 
 // `writer`: this launch is the first of its tile (the one that feeds the exchange)
-int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+// `visit` = position of the tile in time (slot and sequence number of the flag protocol), `tile` = which planes it holds
+int produce(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int visit, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
-  const int slot = slot_of(R, tile);
+  const int slot = slot_of(R, visit);
   const bool fused = E.xmode == XCHG_FUSED;
   // fused: forward, the kernel scatters into the peers' receive slots; backward, it reads this rank's send slot
   void *buf = R.send[slot];
   Launch L = phase == 1 ? L_k1(d, b.U, buf, (long long)tile * d.T1, myT) : L_k3(E, d, b.A, buf, (long long)tile * d.T2, myT);
   if (phase == 2 && E.sched == SCHED_PENCIL) { L.ry_level = 2; L.ry_x0 = 0; L.ry_lo = d.Ry; L.ry_hi = 10; }   // :1708, 1988
-  if (fused && (inverse ? fuse_reader(E, L, phase, tile) : fuse_writer(engs, E, L, phase, tile, myT, inverse))) return -1;
+  if (fused && (inverse ? fuse_reader(E, L, phase, visit) : fuse_writer(engs, E, L, phase, visit, myT, inverse))) return -1;
   L.pdl = E.pdl_next;
   L.depth = E.depth_next;
   return run_launch(E, st, phase == 1 ? ST_K1 : ST_K3, L, inverse);
 }
 
-int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int tile, long long myT, bool inverse, cudaStream_t st) {
+int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, int visit, int tile, long long myT, bool inverse, cudaStream_t st) {
   const Dims d = dims_of(E.po);
   Ring &R = E.ring[phase - 1];
-  const int slot = slot_of(R, tile);
+  const int slot = slot_of(R, visit);
   const bool fused = E.xmode == XCHG_FUSED;
   void *buf = R.recv[slot];
   Launch L = phase == 2 ? L_k4(E, d, buf, b.U, (long long)tile * d.T2, myT) : L_k2(d, buf, b.A, (long long)tile * d.T1, myT);
   if (phase == 1 && E.sched == SCHED_PENCIL) { L.ry_level = 1; L.ry_x0 = tile * d.T1; L.ry_lo = 0; L.ry_hi = d.Ry; }   // :1484
-  if (fused && (inverse ? fuse_writer(engs, E, L, phase, tile, myT, inverse) : fuse_reader(E, L, phase, tile))) return -1;
+  if (fused && (inverse ? fuse_writer(engs, E, L, phase, visit, myT, inverse) : fuse_reader(E, L, phase, visit))) return -1;
   L.pdl = E.pdl_next;
   L.depth = E.depth_next;
   return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
@@ -742,8 +743,22 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   Ring &R0 = E0.ring[phase - 1];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
   const bool fused = E0.xmode == XCHG_FUSED;
-  auto tile_Tk = [&](size_t k, int i) { return std::max<long long>(0, std::min<long long>(tiling, planes[k] - (long long)i * tiling)); };
-  auto tile_T = [&](int i) { return tile_Tk(0, i); };
+  // Which tile is visited i-th.  Forward: ascending.  Backward in phase 1: descending - when the array between the
+  // phases IS the caller's array (_S_ = 1) the reader of a tile rewrites x planes in the input layout, whose plane
+  // stride (istride[0]) is at least that of the planes the writers still have to read (M3*M4*p1); written regions must
+  // therefore trail the read ones, which they do going up in the forward direction and going down in the backward one.
+  // (With equal strides - even divisions - the two coincide plane by plane and the order does not matter; found as a
+  // wrong backward transform of 27x20x45 on 8 real ranks, where istride[0] = 24*M3 against 20*M3.)
+  const bool descending = inverse && phase == 1;
+  auto tile_of = [&](size_t k, int visit) {
+    const int nb = (int)((planes[k] + tiling - 1) / tiling);
+    return visit < nb ? (descending ? nb - 1 - visit : visit) : -1;
+  };
+  auto tile_Tk = [&](size_t k, int visit) {
+    const int t = tile_of(k, visit);
+    return t < 0 ? 0LL : std::max<long long>(0, std::min<long long>(tiling, planes[k] - (long long)t * tiling));
+  };
+  auto tile_T = [&](int visit) { return tile_Tk(0, visit); };
   // fused exchange between processes: readers on the second stream, ordered against the writers by flags alone
   bool two = false;
   E0.narrow_now = false;
@@ -754,9 +769,9 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
       Engine &E = E0;
       E.grid_cap[0] = E.grid_cap[1] = 0;
       E.dry_shape = &shw;
-      int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+      int rc = inverse ? consume(engs, E, bufs[0], phase, 0, tile_of(0, 0), tile_T(0), true, sc) : produce(engs, E, bufs[0], phase, 0, tile_of(0, 0), tile_T(0), false, sc);
       E.dry_shape = &shr;
-      if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_T(0), false, sc);
+      if (!rc) rc = inverse ? produce(engs, E, bufs[0], phase, 0, tile_of(0, 0), tile_T(0), true, sc) : consume(engs, E, bufs[0], phase, 0, tile_of(0, 0), tile_T(0), false, sc);
       E.dry_shape = nullptr;
       if (rc) return -1;
       return plan_overlap(E, shw, shr) ? 1 : 0;
@@ -794,7 +809,10 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   // passed their wait, so at most one grid per stream can be spinning and the grid caps still leave the other
   // stream its share of the SMs.  OFFTB_PDL=0 turns the chains off.
   static const bool pdl_env = !(getenv("OFFTB_PDL") && atoi(getenv("OFFTB_PDL")) == 0);
-  const bool pdl = two && pdl_env;
+  // chained launches may finish out of order; where the reader of one tile rewrites memory next to what the writer of a
+  // neighbouring tile reads (phase 1 in place with unequal plane strides, see `descending`) the writers must finish in order
+  const bool in_place_skew = phase == 1 && bufs[0].A == bufs[0].U && d0.isx != d0.dX;
+  const bool pdl = two && pdl_env && !in_place_skew;
   int n_first = 0, n_second = 0;
   cudaEvent_t ce[4] = {nullptr, nullptr, nullptr, nullptr};
   E0.chain_timing = pdl && E0.stage_timing && !E0.async;
@@ -806,7 +824,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     E.depth_next = 0;
     if (E.chain_timing && !n_first) cudaEventRecord(ce[0], sc);
     ++n_first;
-    return inverse ? consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, sc) : produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, sc);
+    return inverse ? consume(engs, E, bufs[k], phase, i, tile_of(k, i), tile_Tk(k, i), true, sc) : produce(engs, E, bufs[k], phase, i, tile_of(k, i), tile_Tk(k, i), false, sc);
   };
   auto second = [&](size_t k, int i) {
     Engine &E = *engs[k];
@@ -815,7 +833,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
     E.depth_next = two ? E.reader_depth : 0;
     if (E.chain_timing && !n_second) cudaEventRecord(ce[2], s2);
     ++n_second;
-    return inverse ? produce(engs, E, bufs[k], phase, i, tile_Tk(k, i), true, s2) : consume(engs, E, bufs[k], phase, i, tile_Tk(k, i), false, s2);
+    return inverse ? produce(engs, E, bufs[k], phase, i, tile_of(k, i), tile_Tk(k, i), true, s2) : consume(engs, E, bufs[k], phase, i, tile_of(k, i), tile_Tk(k, i), false, s2);
   };
   std::vector<long long> tts(engs.size());
   for (int i = 0; i < blocks; ++i) {

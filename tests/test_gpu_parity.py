@@ -260,6 +260,10 @@ UNEVEN_CASES = [
     ((30, 42, 70), 5, 1, 0, {P.P1: 5, P.S: 1}),
     ((30, 42, 70), 7, 1, 0, {P.P1: 1}),
     ((96, 80, 48), 8, 0, 0, {P.P1: 4, P.T1: 5, P.T2: 7, P.W1: 2, P.W2: 1}),
+    ((27, 20, 45), 8, 1, 0, {P.P1: 1, P.S: 1, P.T1: 4}),        # 8 ranks: shares of 2-3 rows and 5-6 columns
+    ((27, 20, 45), 8, 1, 0, {P.P1: 1, P.S: 1, P.T1: 4, P.W1: 0}),   # in place, plane strides 24*M3 vs 20*M3: the backward tile order matters
+    ((27, 20, 45), 8, 1, 0, {P.P1: 8, P.T2: 2}),
+    ((27, 20, 45), 8, 0, 0, {P.P1: 2, P.S: 1}),
 ]
 
 
