@@ -31,9 +31,13 @@ def cases(p):
            ((32, 64, 64), 1, {P.P1: 1, P.S: 1, P.T1: 5, P.W1: 1}, 64), ((256, 256, 256), 1, {P.P1: p, P.S: 1}, 64),
            ((128, 64, 64), 1, {P.P1: p}, 32),
            # lengths with odd factors and uneven splits: the any-length kernel and the general block split between real ranks
-           ((15, 10, 9), 1, {P.P1: p, P.V: 3, P.T2: 2}, 64), ((27, 20, 45), 1, {P.P1: 1, P.S: 1, P.T1: 4}, 64)]
+           ((15, 10, 9), 1, {P.P1: p, P.V: 3, P.T2: 2}, 64), ((27, 20, 45), 1, {P.P1: 1, P.S: 1, P.T1: 4}, 64),
+           # in place with unequal plane strides on both sides of phase 1 at every p (Ny = 5p+1: planes of 6p rows in the
+           # caller's layout, 5p+1 between the phases) - the backward transform depends on the tile order, plan.cu run_phase
+           ((27, 5 * p + 1, 45), 1, {P.P1: 1, P.S: 1, P.T1: 2, P.W1: 1}, 64)]
     if p >= 4:
-        out += [((10, 9, 15), 0, {P.P1: 2, P.V: 3, P.T1: 2, P.T2: 3}, 64), ((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.Ry: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32)]
+        out += [((10, 9, 15), 0, {P.P1: 2, P.V: 3, P.T1: 2, P.T2: 3}, 64), ((64, 64, 128), 0, {P.P1: 2}, 64), ((64, 128, 64), 0, {P.P1: p // 2, P.S: 1, P.Ry: 3}, 64), ((64, 64, 64), 0, {P.P1: 2, P.T1: 3, P.T2: 5}, 32),
+                ((12, 5 * (p // 2) + 1, 15), 0, {P.P1: 2, P.S: 1, P.T1: 2, P.T2: 4}, 64)]
     return out
 
 

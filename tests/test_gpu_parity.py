@@ -264,6 +264,8 @@ UNEVEN_CASES = [
     ((27, 20, 45), 8, 1, 0, {P.P1: 1, P.S: 1, P.T1: 4, P.W1: 0}),   # in place, plane strides 24*M3 vs 20*M3: the backward tile order matters
     ((27, 20, 45), 8, 1, 0, {P.P1: 8, P.T2: 2}),
     ((27, 20, 45), 8, 0, 0, {P.P1: 2, P.S: 1}),
+    ((27, 11, 45), 2, 1, 0, {P.P1: 1, P.S: 1, P.T1: 2, P.W1: 0}),   # the same skew (12 rows against 11) at p = 2 and in a pencil
+    ((12, 11, 15), 4, 0, 0, {P.P1: 2, P.S: 1, P.T1: 2, P.W1: 0, P.T2: 4, P.W2: 0}),
 ]
 
 
@@ -374,7 +376,9 @@ def test_r2c_plan_matches_reference_fixture(name):
 @pytest.mark.parametrize("N,p,oned,custom,bits", [
     ((64, 32, 128), 1, 0, {P.P1: 1}, 64), ((64, 32, 128), 1, 0, {P.P1: 1, P.S: 1}, 64), ((32, 64, 256), 4, 1, {P.P1: 4}, 64),
     ((32, 64, 250), 4, 1, {P.P1: 1, P.S: 1, P.T1: 5}, 64), ((30, 24, 50), 6, 0, {P.P1: 3, P.V: 3}, 64), ((64, 64, 64), 8, 0, {P.P1: 2, P.T1: 8, P.T2: 5}, 64),
-    ((64, 32, 128), 4, 0, {P.P1: 2}, 32)])
+    ((64, 32, 128), 4, 0, {P.P1: 2}, 32),
+    # in place with unequal plane strides around phase 1 and no slot in flight: forward tiles go up, backward tiles down
+    ((27, 11, 50), 2, 1, {P.P1: 1, P.S: 1, P.T1: 2, P.W1: 0}, 64), ((12, 11, 30), 4, 0, {P.P1: 2, P.S: 1, P.T1: 2, P.W1: 0, P.T2: 4, P.W2: 0}, 64)])
 def test_r2c_matches_numpy_and_round_trips(N, p, oned, custom, bits):
     """half spectrum against numpy.fft.rfftn; the backward transform (complex-to-real) returns N * the real input"""
     _torch()
