@@ -162,11 +162,27 @@ template <typename T> __device__ __forceinline__ void st_global(cx<T> *p, cx<T> 
 #endif
   *p = v;
 }
+// Experiment switches (tools/variants.sh; the shipped build leaves both at 0, see profiles/r02_kernel_ab.md):
+// OFFTB_CPASYNC_L2 = 128 / 256 adds the L2 prefetch-size hint to the ring fills, OFFTB_TILE_CHUNK_LOG = q makes a CTA
+// walk runs of 2^q adjacent tiles (columns next to each other in memory) instead of one tile per round of the grid.
+#ifndef OFFTB_CPASYNC_L2
+#define OFFTB_CPASYNC_L2 0
+#endif
+#ifndef OFFTB_TILE_CHUNK_LOG
+#define OFFTB_TILE_CHUNK_LOG 0
+#endif
+#if OFFTB_CPASYNC_L2 == 256
+#define OFFTB_CPASYNC_HINT ".L2::256B"
+#elif OFFTB_CPASYNC_L2 == 128
+#define OFFTB_CPASYNC_HINT ".L2::128B"
+#else
+#define OFFTB_CPASYNC_HINT ""
+#endif
 __device__ __forceinline__ void cp_async_cx(cx<double> *smem_dst, const cx<double> *gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+  asm volatile("cp.async.cg.shared.global" OFFTB_CPASYNC_HINT " [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_cx(cx<float> *smem_dst, const cx<float> *gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+  asm volatile("cp.async.ca.shared.global" OFFTB_CPASYNC_HINT " [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most `pending` of this thread's groups are still in flight (pending < 4)
@@ -477,10 +493,24 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
   if constexpr (!BULK) {
     // Plain launches: a slot is free again as soon as its tile's exchanges are over, so the ring keeps depth-1 tiles
     // in flight behind the current one.
+#if OFFTB_TILE_CHUNK_LOG > 0
+    // the CTA's k-th tile: runs of 2^q adjacent tiles, the runs dealt round robin over the grid
+    auto tile_at = [&](unsigned k) {
+      return (((k >> OFFTB_TILE_CHUNK_LOG) * gridDim.x + blockIdx.x) << OFFTB_TILE_CHUNK_LOG) | (k & ((1u << OFFTB_TILE_CHUNK_LOG) - 1));
+    };
+    unsigned kth = 0;
+    unsigned tile = tile_at(0);
+    for (int d = 0; d + 1 < depth; ++d) prefetch(tile_at(d), d);
+    int slot = 0;
+    for (; tile < ntiles; tile = tile_at(++kth)) {
+#define OFFTB_TILE_AHEAD(n) tile_at(kth + (unsigned)(n))
+#else
     unsigned tile = blockIdx.x;
     for (int d = 0; d + 1 < depth; ++d) prefetch(tile + d * gridDim.x, d);
     int slot = 0;
     for (; tile < ntiles; tile += gridDim.x) {
+#define OFFTB_TILE_AHEAD(n) (tile + (unsigned)(n) * gridDim.x)
+#endif
       cx<T> *sm = sm_all + slot * slot_elems;
       if (depth == 1) {
         __syncthreads();           // the previous tile's exchange data has been consumed
@@ -499,11 +529,12 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
       if (depth > 1 || CFG::NS > 1 || a.load_cfast != a.store_cfast) __syncthreads();   // the slot now serves as exchange buffer
       if (depth > 1) {
         const int ahead = slot == 0 ? depth - 1 : slot - 1;   // the slot the previous tile has just released
-        prefetch(tile + (unsigned)(depth - 1) * gridDim.x, ahead);
+        prefetch(OFFTB_TILE_AHEAD(depth - 1), ahead);
       }
       transform_tile(v, sm, tile);
       slot = slot + 1 == depth ? 0 : slot + 1;
     }
+#undef OFFTB_TILE_AHEAD
   } else {
     // Bulk-store launches: the slot of the previous tile is still being drained by the TMA engine, so one slot
     // fewer is available for prefetching (depth-2 tiles ahead) and a slot is re-filled only after warp 0 has seen
