@@ -272,9 +272,27 @@ __device__ __forceinline__ cx<T> *out_ptr(const FftArgs &a, void *const *s_tab, 
   return (cx<T> *)s_tab[k >> a.om.n_lg] + (bofs + (long long)(k & ((1 << a.om.n_lg) - 1)) * a.om.n_lo);
 }
 
-template <typename T, class CFG, bool BULK, int S>
+// Long transforms run without a ring (one slot per CTA): the slot is the tile's exchange buffer until the last stage has
+// read its inputs, and from then on - through the last butterflies and all the stores - it is idle.  `early` is called at
+// that point and starts the next tile's fill (kernel body); ON = false compiles it away for the lengths that have a ring.
+template <bool ON, class F> struct EarlyFill {
+  static constexpr bool on = ON;
+  F &f;
+  __device__ __forceinline__ void operator()() const { f(); }
+};
+// Measured (profiles/r02_kernel_ab.md): 1024 points +4..35 %, 2048 points +18..29 %; 4096 points and longer lose (one CTA
+// per SM already streams its stores against the next fill), so the window is 1024..2048.
+#ifndef OFFTB_EARLY_MIN_N
+#define OFFTB_EARLY_MIN_N 1024
+#endif
+#ifndef OFFTB_EARLY_MAX_N
+#define OFFTB_EARLY_MAX_N 2048
+#endif
+
+template <typename T, class CFG, bool BULK, int S, class EARLY>
 __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg, const FftArgs &a, cx<T> *sm,
-                                          void *const *s_tab, long long bofs, unsigned bblock, int t, int s_mul, int s_base, T cj) {
+                                          void *const *s_tab, long long bofs, unsigned bblock, int t, int s_mul, int s_base, T cj,
+                                          const EARLY &early) {
   constexpr int N = CFG::N, E = CFG::E, TT = CFG::T, NS = CFG::NS;
   constexpr int R = CFG::radix(S), NU = E / R, P = CFG::P(S), M = CFG::M(S);
 
@@ -285,6 +303,9 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
       const int beta = t + TT * u;
 #pragma unroll
       for (int i = 0; i < R; ++i) v[u * R + i] = sm[(i * CFG::pitch(S - 1) + beta) * s_mul + s_base];
+    }
+    if constexpr (EARLY::on && S == NS - 1 && !BULK) {
+      if (a.load_cfast == a.store_cfast) early();   // direct stores: nothing reads the slot any more
     }
   }
   // ---- butterflies
@@ -311,7 +332,7 @@ __device__ __forceinline__ void fft_stage(cx<T> (&v)[CFG::E], const cx<T> *wreg,
       }
     }
     __syncthreads();
-    fft_stage<T, CFG, BULK, S + 1>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
+    fft_stage<T, CFG, BULK, S + 1>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj, early);
   } else {
     // ---- last stage: output index beta + (N/R)*k
     if constexpr (BULK) {
@@ -464,6 +485,19 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
     cp_async_commit();
   };
 
+  // ring-less launches (depth 1): the next tile's fill starts as soon as the last stage has its inputs (EarlyFill)
+  constexpr bool EARLY_ON = !BULK && CFG::N >= OFFTB_EARLY_MIN_N && CFG::N <= OFFTB_EARLY_MAX_N && CFG::NS > 1;
+  unsigned next_tile = 0;
+  bool primed = false;
+  auto early_fn = [&]() {
+    if (depth == 1) {
+      __syncthreads();   // every thread has read the last exchange out of the slot
+      prefetch(next_tile, 0);
+      primed = true;
+    }
+  };
+  const EarlyFill<EARLY_ON, decltype(early_fn)> early{early_fn};
+
   // One tile: its E points are in v, the slot `sm` is free to serve as exchange (and, for bulk launches, staging) buffer
   auto transform_tile = [&](cx<T> (&v)[E], cx<T> *sm, unsigned tile) {
     const unsigned bblock = tile << a.c_log;
@@ -476,7 +510,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
       transform = a.ry_lo <= r && r < a.ry_hi;
     }
     if (transform) {
-      fft_stage<T, CFG, BULK, 0>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj);
+      fft_stage<T, CFG, BULK, 0>(v, wreg, a, sm, s_tab, bofs, bblock, t, s_mul, s_base, cj, early);
     } else {
 #pragma unroll
       for (int u = 0; u < NU0; ++u)
@@ -513,8 +547,11 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
 #endif
       cx<T> *sm = sm_all + slot * slot_elems;
       if (depth == 1) {
-        __syncthreads();           // the previous tile's exchange data has been consumed
-        prefetch(tile, 0);
+        if (!(EARLY_ON && primed)) {
+          __syncthreads();         // the previous tile's exchange data has been consumed
+          prefetch(tile, 0);
+        }
+        primed = false;
         cp_async_wait(0);
       } else {
         cp_async_wait(depth - 2);  // this tile has landed (the younger groups may still fly)
@@ -531,6 +568,7 @@ __global__ void __launch_bounds__(CFG::MAXT, CFG::MINB) fft_kernel(const __grid_
         const int ahead = slot == 0 ? depth - 1 : slot - 1;   // the slot the previous tile has just released
         prefetch(OFFTB_TILE_AHEAD(depth - 1), ahead);
       }
+      if constexpr (EARLY_ON) next_tile = OFFTB_TILE_AHEAD(1);
       transform_tile(v, sm, tile);
       slot = slot + 1 == depth ? 0 : slot + 1;
     }
