@@ -280,10 +280,12 @@ template <bool ON, class F> struct EarlyFill {
   F &f;
   __device__ __forceinline__ void operator()() const { f(); }
 };
-// Measured (profiles/r02_kernel_ab.md): 1024 points +4..35 %, 2048 points +18..29 %; 4096 points and longer lose (one CTA
-// per SM already streams its stores against the next fill), so the window is 1024..2048.
+// Measured (profiles/r02_kernel_ab.md): in-place y passes gain (1024 points +7 %, 2048 points +29 %), but the x pass of a
+// 1024^3 grid on one GPU - stores at a 16 MiB plane stride over a 16 GiB array - drops from 4.3 to 3.0 TB/s with the fills
+// queued ahead of its stores, and the launches of the fused exchange were not re-measured with it.  Compile-time
+// experiment (-DOFFTB_EARLY_MIN_N=1024 -DOFFTB_EARLY_MAX_N=2048), off in the shipped build.
 #ifndef OFFTB_EARLY_MIN_N
-#define OFFTB_EARLY_MIN_N 1024
+#define OFFTB_EARLY_MIN_N (1 << 30)
 #endif
 #ifndef OFFTB_EARLY_MAX_N
 #define OFFTB_EARLY_MAX_N 2048
