@@ -98,6 +98,9 @@ int offtb_comm_fill_r2c(struct _offt_comm *c, int Nx, int Ny, int Nz, int p, int
 int offtb_check_supported(int Nx, int Ny, int Nz, int p, int p1);
 /* exchange bookkeeping of one tile: blocks per peer in complex elements (phase 1 or 2) */
 long long offtb_exchange_block_elems(const struct _offt_plan *po, int phase, int myT);
+/* which of a phase's nb tiles the schedule visits i-th (-1: none): ascending, except the backward transform's phase 1,
+ * which goes down so that an in-place exchange never overwrites planes a later tile still reads (plan.cu, run_phase) */
+int offtb_tile_visited(int nb, int visit, int phase, int inverse);
 
 /* ---- built-in search over the tunables (the fetch / report loop of ah_tuning) ---- */
 /* evaluates up to max_loop feasible points on the device and leaves the best in po->params */

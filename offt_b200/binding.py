@@ -81,6 +81,8 @@ def _load():
     L.offtb_plan_last_launches.argtypes = [C.POINTER(OfftPlan)]
     L.offtb_plan_precision.argtypes = [C.POINTER(OfftPlan)]
     L.offtb_plan_stage_ms.argtypes = [C.POINTER(OfftPlan), C.POINTER(d), i]
+    L.offtb_tile_visited.restype = i
+    L.offtb_tile_visited.argtypes = [i, i, i, i]
     L.offtb_exchange_block_elems.restype = ll
     L.offtb_exchange_block_elems.argtypes = [C.POINTER(OfftPlan), i, i]
     L.offtb_fft_rows.restype = d

@@ -726,6 +726,18 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
 //   produce(i); [wait(i-W)]; exchange(i); consume(i-W); ... drain the last W tiles.
 // Forward: produce = K1/K3, consume = K2/K4.  Backward: the same loop with the roles and
 // the ring directions swapped (consume's inverse gathers, produce's inverse scatters).
+// Which of a phase's nb tiles is visited i-th (-1: none).  Forward: ascending.  Backward in phase 1: descending - when
+// the array between the phases IS the caller's array (_S_ = 1) the reader of a tile rewrites x planes in the input layout,
+// whose plane stride (istride[0]) is at least that of the planes the writers still have to read (M3*M4*p1); written regions
+// must therefore trail the read ones, which they do going up in the forward direction and going down in the backward one.
+// (With equal strides - even divisions - the two coincide plane by plane and the order does not matter; found as a wrong
+// backward transform of 27x20x45 on 8 real ranks, where istride[0] = 24*M3 against 20*M3.  tests/test_tile_order.py checks
+// the rule against an interval model of what each launch reads and writes.)
+int tile_visited(int nb, int visit, int phase, bool inverse) {
+  if (visit < 0 || visit >= nb) return -1;
+  return inverse && phase == 1 ? nb - 1 - visit : visit;
+}
+
 int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, bool inverse) {
   Engine &E0 = *engs[0];
   const Dims d0 = dims_of(E0.po);
@@ -743,17 +755,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   Ring &R0 = E0.ring[phase - 1];
   cudaStream_t sc = E0.s_user ? E0.s_user : E0.s_comp, sx = E0.s_comm;
   const bool fused = E0.xmode == XCHG_FUSED;
-  // Which tile is visited i-th.  Forward: ascending.  Backward in phase 1: descending - when the array between the
-  // phases IS the caller's array (_S_ = 1) the reader of a tile rewrites x planes in the input layout, whose plane
-  // stride (istride[0]) is at least that of the planes the writers still have to read (M3*M4*p1); written regions must
-  // therefore trail the read ones, which they do going up in the forward direction and going down in the backward one.
-  // (With equal strides - even divisions - the two coincide plane by plane and the order does not matter; found as a
-  // wrong backward transform of 27x20x45 on 8 real ranks, where istride[0] = 24*M3 against 20*M3.)
-  const bool descending = inverse && phase == 1;
-  auto tile_of = [&](size_t k, int visit) {
-    const int nb = (int)((planes[k] + tiling - 1) / tiling);
-    return visit < nb ? (descending ? nb - 1 - visit : visit) : -1;
-  };
+  auto tile_of = [&](size_t k, int visit) { return tile_visited((int)((planes[k] + tiling - 1) / tiling), visit, phase, inverse); };
   auto tile_Tk = [&](size_t k, int visit) {
     const int t = tile_of(k, visit);
     return t < 0 ? 0LL : std::max<long long>(0, std::min<long long>(tiling, planes[k] - (long long)t * tiling));
@@ -810,7 +812,7 @@ int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, b
   // stream its share of the SMs.  OFFTB_PDL=0 turns the chains off.
   static const bool pdl_env = !(getenv("OFFTB_PDL") && atoi(getenv("OFFTB_PDL")) == 0);
   // chained launches may finish out of order; where the reader of one tile rewrites memory next to what the writer of a
-  // neighbouring tile reads (phase 1 in place with unequal plane strides, see `descending`) the writers must finish in order
+  // neighbouring tile reads (phase 1 in place with unequal plane strides, see tile_visited) the writers must finish in order
   const bool in_place_skew = phase == 1 && bufs[0].A == bufs[0].U && d0.isx != d0.dX;
   const bool pdl = two && pdl_env && !in_place_skew;
   int n_first = 0, n_second = 0;
@@ -1197,3 +1199,6 @@ int engine_execute(std::vector<struct _offt_plan *> &group, std::vector<double *
 }
 
 }  // namespace offtb
+
+// the visit order of run_phase for the host-side model test (tests/test_tile_order.py)
+extern "C" int offtb_tile_visited(int nb, int visit, int phase, int inverse) { return offtb::tile_visited(nb, visit, phase, inverse != 0); }

@@ -266,6 +266,7 @@ UNEVEN_CASES = [
     ((27, 20, 45), 8, 0, 0, {P.P1: 2, P.S: 1}),
     ((27, 11, 45), 2, 1, 0, {P.P1: 1, P.S: 1, P.T1: 2, P.W1: 0}),   # the same skew (12 rows against 11) at p = 2 and in a pencil
     ((12, 11, 15), 4, 0, 0, {P.P1: 2, P.S: 1, P.T1: 2, P.W1: 0, P.T2: 4, P.W2: 0}),
+    ((12, 13, 15), 8, 0, 0, {P.P1: 2, P.S: 1, P.T1: 2, P.W1: 0, P.T2: 2, P.W2: 0}),   # a pencil grid with the skew: 16 rows against 14
 ]
 
 
