@@ -722,10 +722,6 @@ int consume(std::vector<Engine *> &engs, Engine &E, const Bufs &b, int phase, in
   return run_launch(E, st, phase == 2 ? ST_K4 : ST_K2, L, inverse);
 }
 
-// The tile pipeline of offt_3d_execute_phase1/2 (offt-compute.c:3501-3862):
-//   produce(i); [wait(i-W)]; exchange(i); consume(i-W); ... drain the last W tiles.
-// Forward: produce = K1/K3, consume = K2/K4.  Backward: the same loop with the roles and
-// the ring directions swapped (consume's inverse gathers, produce's inverse scatters).
 // Which of a phase's nb tiles is visited i-th (-1: none).  Forward: ascending.  Backward in phase 1: descending - when
 // the array between the phases IS the caller's array (_S_ = 1) the reader of a tile rewrites x planes in the input layout,
 // whose plane stride (istride[0]) is at least that of the planes the writers still have to read (M3*M4*p1); written regions
@@ -738,6 +734,10 @@ int tile_visited(int nb, int visit, int phase, bool inverse) {
   return inverse && phase == 1 ? nb - 1 - visit : visit;
 }
 
+// The tile pipeline of offt_3d_execute_phase1/2 (offt-compute.c:3501-3862):
+//   produce(i); [wait(i-W)]; exchange(i); consume(i-W); ... drain the last W tiles.
+// Forward: produce = K1/K3, consume = K2/K4.  Backward: the same loop with the roles and
+// the ring directions swapped (consume's inverse gathers, produce's inverse scatters).
 int run_phase(std::vector<Engine *> &engs, std::vector<Bufs> &bufs, int phase, bool inverse) {
   Engine &E0 = *engs[0];
   const Dims d0 = dims_of(E0.po);
