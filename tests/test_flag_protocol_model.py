@@ -13,8 +13,8 @@ are past their flag wait) and its own flag condition holds; started launches FIN
 
 The model checks, over random schedules: no deadlock, every reader sees exactly tile s from every member in its slot
 (nothing stale, nothing overwritten early), and flag words only ever grow.  With ONE word per (phase, member) instead of
-one per ring slot - the layout before round 2 - launches finishing out of order make a word go backwards, which the
-last test reproduces."""
+one per ring slot - the layout that was enough while launches ran one after the other, before the dependent-launch
+chains - launches finishing out of order make a word go backwards, which the last test reproduces."""
 import random
 
 import pytest
@@ -100,7 +100,7 @@ def test_per_slot_flags_never_deadlock_never_go_backwards_and_readers_see_their_
 
 
 def test_one_word_per_member_goes_backwards_when_launches_finish_out_of_order():
-    """the layout before round 2: found on real GPUs as a flag time-out of a 2-tile plan"""
+    """the layout from before the chains: found on real GPUs as a flag time-out of a 2-tile plan once launches overlapped"""
     bad = 0
     for seed in range(200):
         w = World(2, 4, 3, per_slot_flags=False, seed=seed)
